@@ -1,0 +1,671 @@
+/*
+ * gais_api.cu -- the C-ABI of include/gais_b200.h over the kernels in gais_kernels.cuh.
+ *
+ * A run (one gais_run_* call = one receiver_run() chunk for every channel, src/receiver.c:87)
+ * is cut into TIME TILES; all DSP/FSM state is carried in ChanState between tiles exactly as
+ * it is carried between runs, so the tiling is invisible in the results (the reference's
+ * output is chunk-size invariant).  Per tile: FIR-sign kernel -> sign words in
+ * a (normally L2-resident) [word][channel] buffer -> tracking kernel (DPLL .. CRC) appending
+ * 64-byte records to per-channel slots.  After the last tile: scan + gather into the dense
+ * (channel, end_bit)-ordered message array.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include <new>
+
+#include "gais_b200.h"
+#include "gais_kernels.cuh"
+#include "gais_fir.cuh"
+#include "gais_track.cuh"
+
+using namespace gais;
+
+static thread_local char tl_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(tl_err, sizeof(tl_err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+	return fail(GAIS_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+extern "C" const char *gais_last_error(void) { return tl_err; }
+extern "C" int gais_abi_version(void) { return GAIS_ABI_VERSION; }
+
+extern "C" int gais_device_count(void)
+{
+	int n = 0, ok = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	for (int i = 0; i < n; i++) {
+		cudaDeviceProp p;
+		if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10)
+			ok++;
+	}
+	return ok;
+}
+
+enum { EV_START = 0, EV_END, EV_POST0, EV_POST1, EV_COUNT };
+
+struct gais_ctx {
+	gais_config cfg;
+	int n_ch;
+	int64_t tile_frames;        /* multiple of 32 */
+	int hist_sel;
+	ChanState *d_state;
+	uint32_t *d_signs[2];       /* [tile words][n_ch] double buffer, or one run-sized buffer (KEEP_SIGNS) */
+	int64_t sign_words;         /* words per channel in each buffer */
+	gais_msg *d_slots;
+	int slot_cap;
+	uint32_t *d_run_count, *d_run_bits;
+	uint64_t *d_offsets;
+	gais_msg *d_dense;
+	int64_t dense_cap;
+	gais_nmea_rec *d_nmea;
+	int64_t nmea_cap;
+	uint32_t *d_bits;
+	int bits_row_words;
+	int32_t *d_overflow;
+	unsigned long long *d_totals;
+	int16_t *d_stage[2];        /* gais_run_host staging tiles */
+	int64_t stage_elems;
+	cudaStream_t s_copy, s_own;
+	cudaEvent_t ev[EV_COUNT], ev_copy[2], ev_free[2];
+	cudaEvent_t *ev_tile;       /* 3 per tile: fir start, fir end / track start, track end */
+	int ev_tile_cap;
+	cudaStream_t last_stream;
+	int pending;                /* a run has been enqueued and not finished */
+	int finished;               /* dense array of the last run is valid */
+	int n_tiles_last;
+	int64_t last_frames;
+	int64_t n_msgs;
+	int launches;
+	gais_timing timing;
+};
+
+static int64_t env_i64(const char *name, int64_t dflt)
+{
+	const char *s = getenv(name);
+	if (!s || !*s)
+		return dflt;
+	return strtoll(s, NULL, 10);
+}
+
+static int upload_taps(void)
+{
+	static const uint32_t half[18] = GAIS_TAP_BITS_HALF;
+	uint32_t full[GAIS_NTAPS];
+	for (int i = 0; i < GAIS_NTAPS; i++)
+		full[i] = half[i < 18 ? i : 35 - i];
+	CK(cudaMemcpyToSymbol(c_taps, full, sizeof(full)));
+	return 0;
+}
+
+extern "C" int gais_reset(gais_ctx *ctx)
+{
+	if (!ctx)
+		return fail(GAIS_EINVAL, "null ctx");
+	CK(cudaSetDevice(ctx->cfg.device));
+	CK(cudaDeviceSynchronize());
+	ChanState init;
+	memset(&init, 0, sizeof(init));
+	init.fsm = GAIS_ST_HUNT;   /* protodec_reset(); everything else is 0 (src/protodec.c:54-100, src/receiver.c:52-74) */
+	/* replicate by doubling copies */
+	CK(cudaMemcpy(ctx->d_state, &init, sizeof(init), cudaMemcpyHostToDevice));
+	for (int64_t have = 1; have < ctx->n_ch; have *= 2) {
+		int64_t n = (have * 2 <= ctx->n_ch) ? have : ctx->n_ch - have;
+		CK(cudaMemcpy(ctx->d_state + have, ctx->d_state, (size_t) n * sizeof(ChanState), cudaMemcpyDeviceToDevice));
+	}
+	CK(cudaMemset(ctx->d_run_count, 0, sizeof(uint32_t) * ctx->n_ch));
+	CK(cudaMemset(ctx->d_run_bits, 0, sizeof(uint32_t) * ctx->n_ch));
+	CK(cudaMemset(ctx->d_overflow, 0, sizeof(int32_t)));
+	ctx->hist_sel = 0;
+	ctx->pending = 0;
+	ctx->finished = 0;
+	ctx->n_msgs = 0;
+	return 0;
+}
+
+extern "C" void gais_destroy(gais_ctx *ctx)
+{
+	if (!ctx)
+		return;
+	cudaSetDevice(ctx->cfg.device);
+	cudaDeviceSynchronize();
+	cudaFree(ctx->d_state);
+	cudaFree(ctx->d_signs[0]);
+	cudaFree(ctx->d_signs[1]);
+	cudaFree(ctx->d_slots);
+	cudaFree(ctx->d_run_count);
+	cudaFree(ctx->d_run_bits);
+	cudaFree(ctx->d_offsets);
+	cudaFree(ctx->d_dense);
+	cudaFree(ctx->d_nmea);
+	cudaFree(ctx->d_bits);
+	cudaFree(ctx->d_overflow);
+	cudaFree(ctx->d_totals);
+	cudaFree(ctx->d_stage[0]);
+	cudaFree(ctx->d_stage[1]);
+	if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+	if (ctx->s_own) cudaStreamDestroy(ctx->s_own);
+	for (int i = 0; i < EV_COUNT; i++)
+		if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+	for (int i = 0; i < 2; i++) {
+		if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+		if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
+	}
+	for (int i = 0; i < ctx->ev_tile_cap; i++)
+		cudaEventDestroy(ctx->ev_tile[i]);
+	free(ctx->ev_tile);
+	delete ctx;
+}
+
+extern "C" int gais_create(const gais_config *cfg, gais_ctx **out)
+{
+	if (!cfg || !out)
+		return fail(GAIS_EINVAL, "null argument");
+	if (cfg->abi_version != GAIS_ABI_VERSION)
+		return fail(GAIS_EINVAL, "abi_version %d != %d", cfg->abi_version, GAIS_ABI_VERSION);
+	if (cfg->n_channels < 1 || cfg->max_frames_per_run < 1)
+		return fail(GAIS_EINVAL, "n_channels and max_frames_per_run must be >= 1");
+	if (cfg->layout != GAIS_LAYOUT_PLANAR && cfg->layout != GAIS_LAYOUT_INTERLEAVED)
+		return fail(GAIS_EINVAL, "unknown layout %d", cfg->layout);
+	if (cfg->fir_mode != GAIS_FIR_GUARD && cfg->fir_mode != GAIS_FIR_EXACT)
+		return fail(GAIS_EINVAL, "unknown fir_mode %d", cfg->fir_mode);
+
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+		cudaGetLastError();
+		return fail(GAIS_ENODEV, "no CUDA device visible: libgaisb200 has no CPU fallback");
+	}
+	if (cfg->device < 0 || cfg->device >= ndev)
+		return fail(GAIS_ENODEV, "device %d out of range (0..%d)", cfg->device, ndev - 1);
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, cfg->device));
+	if (prop.major != 10)
+		return fail(GAIS_ENODEV, "device %d is sm_%d%d; this library carries sm_100a code only", cfg->device,
+			    prop.major, prop.minor);
+	CK(cudaSetDevice(cfg->device));
+
+	gais_ctx *ctx = new (std::nothrow) gais_ctx();
+	if (!ctx)
+		return fail(GAIS_ENOMEM, "out of host memory");
+	memset(ctx, 0, sizeof(*ctx));
+	ctx->cfg = *cfg;
+	ctx->n_ch = cfg->n_channels;
+
+	int64_t tile = env_i64("GAIS_TILE_FRAMES", 0);
+	if (cfg->reserved[1] > 0)
+		tile = cfg->reserved[1];
+	if (tile <= 0) {
+		/* default: keep one tile of sign words (n_ch * tile / 8 bytes) around 32 MB so it
+		 * lives in the 126 MB L2 between the FIR and the tracking kernel */
+		tile = (int64_t) 32 * 1024 * 1024 * 8 / ctx->n_ch;
+		if (tile > 65536) tile = 65536;
+		if (tile < 2048) tile = 2048;
+	}
+	tile = (tile + 1023) / 1024 * 1024;
+	ctx->tile_frames = tile;
+
+	int rc = 0;
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+	rc = fail(e_ == cudaErrorMemoryAllocation ? GAIS_ENOMEM : GAIS_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); goto bad; } } while (0)
+
+	{
+		int64_t run_frames = cfg->max_frames_per_run;
+		if (cfg->flags & GAIS_KEEP_SIGNS) {
+			ctx->sign_words = ((run_frames + tile - 1) / tile) * (tile / 32);
+			CKC(cudaMalloc(&ctx->d_signs[0], (size_t) ctx->sign_words * ctx->n_ch * 4));
+		} else {
+			ctx->sign_words = tile / 32;
+			CKC(cudaMalloc(&ctx->d_signs[0], (size_t) ctx->sign_words * ctx->n_ch * 4));
+			CKC(cudaMalloc(&ctx->d_signs[1], (size_t) ctx->sign_words * ctx->n_ch * 4));
+		}
+		ctx->slot_cap = cfg->reserved[0] > 0 ? cfg->reserved[0] : (int) (run_frames / 1280 + run_frames / 5120 + 8);
+		CKC(cudaMalloc(&ctx->d_state, (size_t) ctx->n_ch * sizeof(ChanState)));
+		CKC(cudaMalloc(&ctx->d_slots, (size_t) ctx->n_ch * ctx->slot_cap * sizeof(gais_msg)));
+		CKC(cudaMalloc(&ctx->d_run_count, (size_t) ctx->n_ch * 4));
+		CKC(cudaMalloc(&ctx->d_run_bits, (size_t) ctx->n_ch * 4));
+		CKC(cudaMalloc(&ctx->d_offsets, (size_t) (ctx->n_ch + 1) * 8));
+		CKC(cudaMalloc(&ctx->d_overflow, 4));
+		CKC(cudaMalloc(&ctx->d_totals, 3 * 8));
+		if (cfg->flags & GAIS_KEEP_BITS) {
+			/* the DPLL advances at most (13107 + 819) / 65536 bit per sample */
+			int64_t max_bits = run_frames * 13926 / 65536 + 2;
+			ctx->bits_row_words = (int) ((max_bits + 31) / 32);
+			CKC(cudaMalloc(&ctx->d_bits, (size_t) ctx->n_ch * ctx->bits_row_words * 4));
+		}
+		CKC(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
+		CKC(cudaStreamCreateWithFlags(&ctx->s_own, cudaStreamNonBlocking));
+		for (int i = 0; i < EV_COUNT; i++)
+			CKC(cudaEventCreate(&ctx->ev[i]));
+		for (int i = 0; i < 2; i++) {
+			CKC(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
+			CKC(cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
+		}
+	}
+	if ((rc = upload_taps()) != 0)
+		goto bad;
+	if ((rc = fir_setup()) != 0) {
+		rc = fail(GAIS_ECUDA, "fir_setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+		goto bad;
+	}
+	if ((rc = gais_reset(ctx)) != 0)
+		goto bad;
+	*out = ctx;
+	return 0;
+bad:
+	gais_destroy(ctx);
+	return rc;
+#undef CKC
+}
+
+static int ensure_tile_events(gais_ctx *ctx, int n_tiles)
+{
+	int need = n_tiles * 3;
+	if (need <= ctx->ev_tile_cap)
+		return 0;
+	cudaEvent_t *ne = (cudaEvent_t *) realloc(ctx->ev_tile, sizeof(cudaEvent_t) * need);
+	if (!ne)
+		return fail(GAIS_ENOMEM, "out of host memory");
+	ctx->ev_tile = ne;
+	for (int i = ctx->ev_tile_cap; i < need; i++) {
+		CK(cudaEventCreate(&ctx->ev_tile[i]));
+		ctx->ev_tile_cap = i + 1;
+	}
+	return 0;
+}
+
+/* enqueue FIR + tracking for one time tile whose samples are at `view` (n = 0 is the first
+ * sample of the tile) */
+static int enqueue_tile(gais_ctx *ctx, SampleView view, int64_t n_frames, int tile_idx, int64_t word_ofs, cudaStream_t st,
+			bool timed)
+{
+	uint32_t *signs;
+	if (ctx->cfg.flags & GAIS_KEEP_SIGNS)
+		signs = ctx->d_signs[0] + word_ofs * ctx->n_ch;
+	else
+		signs = ctx->d_signs[tile_idx & 1];
+
+	if (timed) CK(cudaEventRecord(ctx->ev_tile[3 * tile_idx + 0], st));
+	int nl = fir_launch(ctx->cfg.fir_mode, ctx->cfg.layout, view, ctx->d_state, ctx->hist_sel, ctx->n_ch, n_frames, signs, st);
+	if (nl < 0)
+		return fail(GAIS_ECUDA, "FIR launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+	ctx->launches += nl;
+	save_hist_kernel<<<(ctx->n_ch + 127) / 128, 128, 0, st>>>(view, ctx->d_state, ctx->hist_sel, ctx->n_ch, n_frames);
+	ctx->launches++;
+	ctx->hist_sel ^= 1;
+	if (timed) CK(cudaEventRecord(ctx->ev_tile[3 * tile_idx + 1], st));
+
+	TrackOut out;
+	out.slots = ctx->d_slots;
+	out.run_count = ctx->d_run_count;
+	out.bits = ctx->d_bits;
+	out.run_bits = ctx->d_run_bits;
+	out.slot_cap = ctx->slot_cap;
+	out.bits_row_words = ctx->bits_row_words;
+	out.overflow = ctx->d_overflow;
+	nl = track_launch(signs, ctx->d_state, ctx->n_ch, n_frames, out, st);
+	if (nl < 0)
+		return fail(GAIS_ECUDA, "tracking launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+	ctx->launches += nl;
+	if (timed) CK(cudaEventRecord(ctx->ev_tile[3 * tile_idx + 2], st));
+	CK(cudaGetLastError());
+	return 0;
+}
+
+static int begin_run(gais_ctx *ctx, int64_t n_frames, cudaStream_t st)
+{
+	if (n_frames < 1 || n_frames > ctx->cfg.max_frames_per_run)
+		return fail(GAIS_EINVAL, "n_frames %lld outside 1..max_frames_per_run (%lld)", (long long) n_frames,
+			    (long long) ctx->cfg.max_frames_per_run);
+	CK(cudaSetDevice(ctx->cfg.device));
+	ctx->launches = 0;
+	ctx->finished = 0;
+	ctx->last_frames = n_frames;
+	CK(cudaMemsetAsync(ctx->d_run_count, 0, sizeof(uint32_t) * ctx->n_ch, st));
+	CK(cudaMemsetAsync(ctx->d_run_bits, 0, sizeof(uint32_t) * ctx->n_ch, st));
+	return 0;
+}
+
+extern "C" int gais_run_device(gais_ctx *ctx, const int16_t *d_samples, int64_t n_frames, int64_t stride, void *stream)
+{
+	if (!ctx || !d_samples)
+		return fail(GAIS_EINVAL, "null argument");
+	cudaStream_t st = (cudaStream_t) stream;
+	int rc = begin_run(ctx, n_frames, st);
+	if (rc)
+		return rc;
+	const bool planar = ctx->cfg.layout == GAIS_LAYOUT_PLANAR;
+	if (planar ? stride < n_frames : stride < ctx->n_ch)
+		return fail(GAIS_EINVAL, "stride %lld too small for the layout", (long long) stride);
+
+	int n_tiles = (int) ((n_frames + ctx->tile_frames - 1) / ctx->tile_frames);
+	if ((rc = ensure_tile_events(ctx, n_tiles)) != 0)
+		return rc;
+	CK(cudaEventRecord(ctx->ev[EV_START], st));
+	for (int t = 0; t < n_tiles; t++) {
+		int64_t f0 = (int64_t) t * ctx->tile_frames;
+		int64_t nf = (n_frames - f0 < ctx->tile_frames) ? n_frames - f0 : ctx->tile_frames;
+		SampleView v;
+		v.ch_stride = planar ? stride : 1;
+		v.t_stride = planar ? 1 : stride;
+		v.base = d_samples + f0 * v.t_stride;
+		if ((rc = enqueue_tile(ctx, v, nf, t, f0 / 32, st, true)) != 0)
+			return rc;
+	}
+	scan_counts_kernel<<<1, 1024, 0, st>>>(ctx->d_run_count, ctx->n_ch, ctx->d_offsets);
+	ctx->launches++;
+	CK(cudaEventRecord(ctx->ev[EV_END], st));
+	CK(cudaGetLastError());
+	ctx->last_stream = st;
+	ctx->pending = 1;
+	ctx->n_tiles_last = n_tiles;
+	return 0;
+}
+
+extern "C" int gais_run_host(gais_ctx *ctx, const int16_t *h_samples, int64_t n_frames, int64_t stride)
+{
+	if (!ctx || !h_samples)
+		return fail(GAIS_EINVAL, "null argument");
+	cudaStream_t st = ctx->s_own;
+	int rc = begin_run(ctx, n_frames, st);
+	if (rc)
+		return rc;
+	const bool planar = ctx->cfg.layout == GAIS_LAYOUT_PLANAR;
+	if (planar ? stride < n_frames : stride < ctx->n_ch)
+		return fail(GAIS_EINVAL, "stride %lld too small for the layout", (long long) stride);
+
+	/* staging tiles: planar [n_ch][tile] (device stride = tile), interleaved [tile][stride] */
+	int64_t tile = ctx->tile_frames;
+	int64_t need = planar ? (int64_t) ctx->n_ch * tile : tile * stride;
+	if (need > ctx->stage_elems) {
+		CK(cudaStreamSynchronize(ctx->s_copy));
+		CK(cudaStreamSynchronize(st));
+		cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]);
+		ctx->d_stage[0] = ctx->d_stage[1] = NULL;
+		ctx->stage_elems = 0;
+		CK(cudaMalloc(&ctx->d_stage[0], (size_t) need * 2));
+		CK(cudaMalloc(&ctx->d_stage[1], (size_t) need * 2));
+		ctx->stage_elems = need;
+		CK(cudaEventRecord(ctx->ev_free[0], st));
+		CK(cudaEventRecord(ctx->ev_free[1], st));
+	}
+	int n_tiles = (int) ((n_frames + tile - 1) / tile);
+	if ((rc = ensure_tile_events(ctx, n_tiles)) != 0)
+		return rc;
+	CK(cudaEventRecord(ctx->ev[EV_START], st));
+	for (int t = 0; t < n_tiles; t++) {
+		int64_t f0 = (int64_t) t * tile;
+		int64_t nf = (n_frames - f0 < tile) ? n_frames - f0 : tile;
+		int b = t & 1;
+		/* the copy into buffer b must wait until the kernels of tile t-2 have read it */
+		CK(cudaStreamWaitEvent(ctx->s_copy, ctx->ev_free[b], 0));
+		SampleView v;
+		if (planar) {
+			CK(cudaMemcpy2DAsync(ctx->d_stage[b], (size_t) tile * 2, h_samples + f0, (size_t) stride * 2, (size_t) nf * 2,
+					     (size_t) ctx->n_ch, cudaMemcpyHostToDevice, ctx->s_copy));
+			v.base = ctx->d_stage[b]; v.ch_stride = tile; v.t_stride = 1;
+		} else {
+			CK(cudaMemcpyAsync(ctx->d_stage[b], h_samples + f0 * stride, (size_t) nf * stride * 2, cudaMemcpyHostToDevice,
+					   ctx->s_copy));
+			v.base = ctx->d_stage[b]; v.ch_stride = 1; v.t_stride = stride;
+		}
+		CK(cudaEventRecord(ctx->ev_copy[b], ctx->s_copy));
+		CK(cudaStreamWaitEvent(st, ctx->ev_copy[b], 0));
+		if ((rc = enqueue_tile(ctx, v, nf, t, f0 / 32, st, true)) != 0)
+			return rc;
+		CK(cudaEventRecord(ctx->ev_free[b], st));
+	}
+	scan_counts_kernel<<<1, 1024, 0, st>>>(ctx->d_run_count, ctx->n_ch, ctx->d_offsets);
+	ctx->launches++;
+	CK(cudaEventRecord(ctx->ev[EV_END], st));
+	CK(cudaGetLastError());
+	ctx->last_stream = st;
+	ctx->pending = 1;
+	ctx->n_tiles_last = n_tiles;
+	return 0;
+}
+
+/* complete the last run: wait, size and fill the dense message array */
+static int finish(gais_ctx *ctx)
+{
+	CK(cudaSetDevice(ctx->cfg.device));
+	if (!ctx->pending)
+		return 0;
+	cudaStream_t st = ctx->last_stream;
+	uint64_t total = 0;
+	int32_t ovf = 0;
+	CK(cudaMemcpyAsync(&total, ctx->d_offsets + ctx->n_ch, 8, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(&ovf, ctx->d_overflow, 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	if ((int64_t) total > ctx->dense_cap) {
+		cudaFree(ctx->d_dense);
+		ctx->d_dense = NULL;
+		ctx->dense_cap = 0;
+		int64_t cap = (int64_t) total + (int64_t) total / 8 + 1024;
+		CK(cudaMalloc(&ctx->d_dense, (size_t) cap * sizeof(gais_msg)));
+		ctx->dense_cap = cap;
+	}
+	CK(cudaEventRecord(ctx->ev[EV_POST0], st));
+	if (total > 0) {
+		int64_t threads = (int64_t) ctx->n_ch * 32;
+		gather_msgs_kernel<<<(unsigned) ((threads + 255) / 256), 256, 0, st>>>(ctx->d_slots, ctx->slot_cap, ctx->d_run_count,
+										      ctx->d_offsets, ctx->n_ch, ctx->d_dense);
+		ctx->launches++;
+	}
+	CK(cudaEventRecord(ctx->ev[EV_POST1], st));
+	CK(cudaStreamSynchronize(st));
+	CK(cudaGetLastError());
+	ctx->n_msgs = (int64_t) total;
+	ctx->pending = 0;
+	ctx->finished = 1;
+
+	gais_timing &tm = ctx->timing;
+	memset(&tm, 0, sizeof(tm));
+	float ms = 0;
+	CK(cudaEventElapsedTime(&ms, ctx->ev[EV_START], ctx->ev[EV_END]));
+	tm.total_ms = ms;
+	for (int t = 0; t < ctx->n_tiles_last; t++) {
+		CK(cudaEventElapsedTime(&ms, ctx->ev_tile[3 * t], ctx->ev_tile[3 * t + 1]));
+		tm.fir_ms += ms;
+		CK(cudaEventElapsedTime(&ms, ctx->ev_tile[3 * t + 1], ctx->ev_tile[3 * t + 2]));
+		tm.track_ms += ms;
+	}
+	CK(cudaEventElapsedTime(&ms, ctx->ev[EV_POST0], ctx->ev[EV_POST1]));
+	tm.post_ms = ms;
+	tm.total_ms += ms;
+	tm.launches = ctx->launches;
+	if (ovf) {
+		CK(cudaMemset(ctx->d_overflow, 0, 4));
+		return fail(GAIS_EOVERFLOW, "a channel produced more than %d messages in one run (raise reserved[0])", ctx->slot_cap);
+	}
+	return 0;
+}
+
+extern "C" int gais_sync(gais_ctx *ctx)
+{
+	if (!ctx)
+		return fail(GAIS_EINVAL, "null ctx");
+	return finish(ctx);
+}
+
+extern "C" int gais_message_count(gais_ctx *ctx, int64_t *n_msgs)
+{
+	if (!ctx || !n_msgs)
+		return fail(GAIS_EINVAL, "null argument");
+	int rc = finish(ctx);
+	*n_msgs = ctx->n_msgs;
+	return rc;
+}
+
+extern "C" int gais_device_messages(gais_ctx *ctx, const gais_msg **d_msgs, int64_t *n_msgs)
+{
+	if (!ctx || !d_msgs || !n_msgs)
+		return fail(GAIS_EINVAL, "null argument");
+	int rc = finish(ctx);
+	*d_msgs = ctx->d_dense;
+	*n_msgs = ctx->n_msgs;
+	return rc;
+}
+
+extern "C" int gais_get_messages(gais_ctx *ctx, gais_msg *h_out, int64_t cap, int64_t *n_msgs)
+{
+	if (!ctx || !n_msgs)
+		return fail(GAIS_EINVAL, "null argument");
+	int rc = finish(ctx);
+	*n_msgs = ctx->n_msgs;
+	if (rc)
+		return rc;
+	int64_t n = ctx->n_msgs < cap ? ctx->n_msgs : cap;
+	if (n > 0 && h_out)
+		CK(cudaMemcpy(h_out, ctx->d_dense, (size_t) n * sizeof(gais_msg), cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+extern "C" int gais_get_nmea(gais_ctx *ctx, gais_nmea_rec *h_out, int64_t cap, int64_t *n_msgs)
+{
+	if (!ctx || !n_msgs)
+		return fail(GAIS_EINVAL, "null argument");
+	int rc = finish(ctx);
+	*n_msgs = ctx->n_msgs;
+	if (rc)
+		return rc;
+	int64_t n = ctx->n_msgs < cap ? ctx->n_msgs : cap;
+	if (n <= 0 || !h_out)
+		return 0;
+	if (ctx->n_msgs > ctx->nmea_cap) {
+		cudaFree(ctx->d_nmea);
+		ctx->d_nmea = NULL;
+		ctx->nmea_cap = 0;
+		CK(cudaMalloc(&ctx->d_nmea, (size_t) ctx->n_msgs * sizeof(gais_nmea_rec)));
+		ctx->nmea_cap = ctx->n_msgs;
+	}
+	nmea_kernel<<<(unsigned) ((ctx->n_msgs + 127) / 128), 128>>>(ctx->d_dense, ctx->n_msgs, ctx->d_nmea);
+	CK(cudaGetLastError());
+	CK(cudaMemcpy(h_out, ctx->d_nmea, (size_t) n * sizeof(gais_nmea_rec), cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+struct StateRow { gais_counters cnt; gais_chan_state st; };
+
+__global__ void export_state_kernel(const ChanState *__restrict__ st, int n, gais_counters *cnt, gais_chan_state *cs)
+{
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= n)
+		return;
+	if (cnt) {
+		cnt[c].ok = st[c].ok; cnt[c].crcfail = st[c].crcfail; cnt[c].sizefail = st[c].sizefail;
+	}
+	if (cs) {
+		cs[c].pll = st[c].pll; cs[c].prev = st[c].prev; cs[c].lastbit = st[c].lastbit;
+		cs[c].fsm_state = st[c].fsm; cs[c].seqnr = st[c].seqnr; cs[c].n_bits = st[c].n_bits;
+	}
+}
+
+static int export_state(gais_ctx *ctx, gais_counters *h_cnt, gais_chan_state *h_cs)
+{
+	int rc = finish(ctx);
+	if (rc && rc != GAIS_EOVERFLOW)
+		return rc;
+	void *d = NULL;
+	size_t bytes = (size_t) ctx->n_ch * (h_cnt ? sizeof(gais_counters) : sizeof(gais_chan_state));
+	CK(cudaMalloc(&d, bytes));
+	export_state_kernel<<<(ctx->n_ch + 127) / 128, 128>>>(ctx->d_state, ctx->n_ch, h_cnt ? (gais_counters *) d : NULL,
+							       h_cs ? (gais_chan_state *) d : NULL);
+	cudaError_t e = cudaMemcpy(h_cnt ? (void *) h_cnt : (void *) h_cs, d, bytes, cudaMemcpyDeviceToHost);
+	cudaFree(d);
+	CK(e);
+	return 0;
+}
+
+extern "C" int gais_get_counters(gais_ctx *ctx, gais_counters *h_out)
+{
+	if (!ctx || !h_out)
+		return fail(GAIS_EINVAL, "null argument");
+	return export_state(ctx, h_out, NULL);
+}
+
+extern "C" int gais_get_state(gais_ctx *ctx, gais_chan_state *h_out)
+{
+	if (!ctx || !h_out)
+		return fail(GAIS_EINVAL, "null argument");
+	return export_state(ctx, NULL, h_out);
+}
+
+extern "C" int gais_get_totals(gais_ctx *ctx, int64_t totals[3])
+{
+	if (!ctx || !totals)
+		return fail(GAIS_EINVAL, "null argument");
+	int rc = finish(ctx);
+	if (rc && rc != GAIS_EOVERFLOW)
+		return rc;
+	CK(cudaMemset(ctx->d_totals, 0, 24));
+	totals_kernel<<<(ctx->n_ch + 255) / 256, 256>>>(ctx->d_state, ctx->n_ch, ctx->d_totals);
+	CK(cudaMemcpy(totals, ctx->d_totals, 24, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+extern "C" int gais_bits_row_words(gais_ctx *ctx, int64_t *words_per_row)
+{
+	if (!ctx || !words_per_row)
+		return fail(GAIS_EINVAL, "null argument");
+	*words_per_row = ctx->bits_row_words;
+	return 0;
+}
+
+extern "C" int gais_get_bits(gais_ctx *ctx, uint32_t *h_words, uint32_t *h_nbits)
+{
+	if (!ctx || !h_words || !h_nbits)
+		return fail(GAIS_EINVAL, "null argument");
+	if (!ctx->d_bits)
+		return fail(GAIS_EINVAL, "context was created without GAIS_KEEP_BITS");
+	int rc = finish(ctx);
+	if (rc && rc != GAIS_EOVERFLOW)
+		return rc;
+	CK(cudaMemcpy(h_words, ctx->d_bits, (size_t) ctx->n_ch * ctx->bits_row_words * 4, cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(h_nbits, ctx->d_run_bits, (size_t) ctx->n_ch * 4, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+extern "C" int gais_get_signs(gais_ctx *ctx, uint32_t *h_words, int64_t cap_words)
+{
+	if (!ctx || !h_words)
+		return fail(GAIS_EINVAL, "null argument");
+	if (!(ctx->cfg.flags & GAIS_KEEP_SIGNS))
+		return fail(GAIS_EINVAL, "context was created without GAIS_KEEP_SIGNS");
+	int rc = finish(ctx);
+	if (rc && rc != GAIS_EOVERFLOW)
+		return rc;
+	int64_t words = ((ctx->last_frames + 31) / 32) * ctx->n_ch;
+	if (words > cap_words)
+		words = cap_words;
+	CK(cudaMemcpy(h_words, ctx->d_signs[0], (size_t) words * 4, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+extern "C" int gais_get_timing(gais_ctx *ctx, gais_timing *out)
+{
+	if (!ctx || !out)
+		return fail(GAIS_EINVAL, "null argument");
+	int rc = finish(ctx);
+	*out = ctx->timing;
+	return rc;
+}
+
+extern "C" int gais_nmea_format(const gais_msg *msg, char *out)
+{
+	if (!msg || !out)
+		return fail(GAIS_EINVAL, "null argument");
+	return gn_format(msg->payload, msg->nbits, msg->flags & 15, out);
+}

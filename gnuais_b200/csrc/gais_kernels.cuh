@@ -1,0 +1,399 @@
+/*
+ * gais_kernels.cuh -- sm_100a kernels of the batched AIS receive path.
+ *
+ *   fir_sign_kernel   K1  int16 -> 36-tap FIR -> sign bit per sample (32 samples / word)
+ *   save_hist_kernel      carries the last 36 samples of the run into the next one
+ *   track_kernel      K2+K3  zero-crossing DPLL, slicer, NRZI, HDLC FSM, CRC-16, records
+ *   scan/gather       K4  dense (channel, end_bit)-ordered message array
+ *   nmea_kernel       K5  !AIVDM armouring on the GPU
+ *
+ * Reference behaviour each kernel reproduces is cited at the kernel.
+ */
+#ifndef GAIS_KERNELS_CUH
+#define GAIS_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gais_b200.h"
+#include "gais_state.h"
+#include "gais_nmea.h"
+
+namespace gais {
+
+__constant__ float c_taps[GAIS_NTAPS];
+
+/* sample (c, n) of the run; n < 0 reads the carried history x[n_prev_end + n] */
+struct SampleView {
+	const int16_t *base;
+	int64_t ch_stride, t_stride;
+};
+
+/* ------------------------------------------------------------------------------------------
+ * K1 (exact flavour).  out[n] = sum_{i<36} tap[i] * x[n-36+i]  -- the window is the 36 samples
+ * BEFORE the one just stored (src/filter.c:115-125) -- as a float32 sum, multiply then add,
+ * strictly in tap order (src/filter.h:40-49), no FMA contraction, denormals honoured.  Only
+ * (out[n] > 0) is ever consumed (src/receiver.c:110-111,126).  Taps 0,1,34,35 are exactly
+ * +0.0f: their products are +-0 and s + (+-0) == s for every s this sum can reach (s is never
+ * -0), so they are skipped.
+ *
+ * Block = 8 warps = 8 adjacent channels x one 1024-sample tile; lane l owns outputs
+ * [32l, 32l+32) of its warp's channel -> one sign word.  signs layout: [word][channel].
+ * ------------------------------------------------------------------------------------------ */
+constexpr int K1_CH = 8;
+constexpr int K1_TILE = 1024;
+constexpr int K1_ROW = K1_TILE + GAIS_NTAPS + 4;   /* int16 elements per smem row (padded) */
+
+__device__ __forceinline__ float exact_fir(const float *xs /* 36 window values */)
+{
+	float s = 0.0f;
+#pragma unroll
+	for (int i = 2; i < GAIS_NTAPS - 2; i++)
+		s = __fadd_rn(s, __fmul_rn(xs[i], c_taps[i]));
+	return s;
+}
+
+__global__ void __launch_bounds__(K1_CH * 32)
+fir_sign_exact_kernel(SampleView in, const ChanState *__restrict__ st, int hist_sel,
+		      int n_channels, int64_t n_frames, uint32_t *__restrict__ signs)
+{
+	__shared__ int16_t tile[K1_CH][K1_ROW];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int c = blockIdx.x * K1_CH + warp;
+	const int64_t n0 = (int64_t) blockIdx.y * K1_TILE;
+
+	if (c < n_channels) {
+		const int16_t *row = in.base + (int64_t) c * in.ch_stride;
+		for (int i = lane; i < K1_TILE + GAIS_NTAPS; i += 32) {
+			int64_t n = n0 - GAIS_NTAPS + i;
+			int16_t v = 0;
+			if (n < 0)
+				v = st[c].hist[hist_sel][GAIS_NTAPS + n];
+			else if (n < n_frames)
+				v = row[n * in.t_stride];
+			tile[warp][i] = v;
+		}
+	}
+	__syncwarp();
+	if (c >= n_channels)
+		return;
+	if (n0 + 32 * lane >= n_frames)
+		return;
+
+	float xs[GAIS_NTAPS + 31];
+#pragma unroll
+	for (int i = 0; i < GAIS_NTAPS + 31; i++)
+		xs[i] = (float) tile[warp][32 * lane + i];
+
+	uint32_t word = 0;
+#pragma unroll
+	for (int j = 0; j < 32; j++) {
+		float s = exact_fir(&xs[j]);
+		word |= (s > 0.0f ? 1u : 0u) << j;
+	}
+	signs[((int64_t) blockIdx.y * 32 + lane) * n_channels + c] = word;
+}
+
+/* next run's history = last 36 samples seen (src/filter.c:129-134 keeps exactly these) */
+__global__ void save_hist_kernel(SampleView in, ChanState *st, int hist_sel, int n_channels, int64_t n_frames)
+{
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= n_channels)
+		return;
+	const int16_t *row = in.base + (int64_t) c * in.ch_stride;
+	for (int i = 0; i < GAIS_NTAPS; i++) {
+		int64_t n = n_frames - GAIS_NTAPS + i;
+		st[c].hist[hist_sel ^ 1][i] = (n < 0) ? st[c].hist[hist_sel][GAIS_NTAPS + n] : row[n * in.t_stride];
+	}
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K2+K3.  One lane per channel, sequential in time.
+ *   DPLL/slicer/NRZI: src/receiver.c:109-135.  HDLC FSM: src/protodec.c:988-1122.
+ *   CRC: src/protodec.c:106-167.  type gate + seqnr: src/protodec.c:896-929.
+ * ------------------------------------------------------------------------------------------ */
+struct TrackOut {
+	gais_msg *slots;          /* [n_channels][slot_cap] */
+	uint32_t *run_count;      /* [n_channels] messages written this run */
+	uint32_t *bits;           /* [n_channels][bits_row_words] or NULL */
+	uint32_t *run_bits;       /* [n_channels] bits produced this run */
+	int32_t slot_cap;
+	int32_t bits_row_words;
+	int32_t *overflow;        /* set to 1 if a channel ran out of slots */
+};
+
+struct Fsm {
+	uint32_t fsm, stuffed, last, nflag, nones, nalt, pos, seqnr;
+	uint32_t store[GAIS_STORE_WORDS];
+	int32_t ok, crcfail, sizefail;
+};
+
+__device__ __forceinline__ void fsm_reset(Fsm &f)   /* src/protodec.c:87-100 */
+{
+	f.fsm = GAIS_ST_HUNT;
+	f.nflag = 0; f.nalt = 0; f.nones = 0; f.last = 0; f.stuffed = 0; f.pos = 0;
+}
+
+__device__ __forceinline__ uint32_t crc16_x25_bytes(const uint32_t *store, int nbytes)
+{
+	/* bitwise, LSB first, init 0xffff, poly 0x8408; returns ~crc (src/protodec.c:106-118) */
+	uint32_t crc = 0xffffu;
+	for (int k = 0; k < nbytes * 8; k++) {
+		uint32_t bit = (store[k >> 5] >> (k & 31)) & 1u;
+		crc = ((crc ^ bit) & 1u) ? (crc >> 1) ^ 0x8408u : crc >> 1;
+	}
+	return (~crc) & 0xffffu;
+}
+
+__device__ __noinline__ void frame_end(Fsm &f, uint32_t b, uint32_t bit_index, int c, uint32_t &nmsg, const TrackOut &out)
+{
+	int nbits = (int) f.pos - 22;                         /* src/protodec.c:1096 */
+	if (b == 0 && nbits > 0) {
+		int nb = nbits >> 3;
+		if (crc16_x25_bytes(f.store, nb + 2) == 0x0f47u) { /* src/protodec.c:146,166 */
+			f.ok++;
+			if (nmsg < (uint32_t) out.slot_cap) {
+				uint32_t *w = reinterpret_cast<uint32_t *>(&out.slots[(int64_t) c * out.slot_cap + nmsg]);
+				uint32_t type = (f.store[0] & 0xffu) >> 2;
+				uint32_t gate = (type >= 1 && type <= 24) ? 1u : 0u;
+				uint32_t flags = f.seqnr | (gate << 4);
+#pragma unroll
+				for (int i = 0; i < 13; i++) {
+					int lo = 32 * i;
+					uint32_t v = f.store[i];
+					/* keep only the nb payload bytes */
+					if (8 * nb <= lo) v = 0;
+					else if (8 * nb < lo + 32) v &= (1u << (8 * nb - lo)) - 1u;
+					w[i] = v;
+				}
+				{
+					uint32_t v = (nb > 52) ? (f.store[13] & 0xffu) : 0u;   /* payload[52] */
+					w[13] = v | (flags << 8) | ((uint32_t) nbits << 16);
+				}
+				w[14] = (uint32_t) c;
+				w[15] = bit_index;
+				if (gate)
+					f.seqnr = (f.seqnr + 1u) % 10u;               /* src/protodec.c:924-926 */
+				nmsg++;
+			} else {
+				/* still advance seqnr so later records stay right; flag the overflow */
+				uint32_t type = (f.store[0] & 0xffu) >> 2;
+				if (type >= 1 && type <= 24)
+					f.seqnr = (f.seqnr + 1u) % 10u;
+				*out.overflow = 1;
+			}
+		} else {
+			f.crcfail++;
+		}
+	} else {
+		f.sizefail++;
+	}
+	fsm_reset(f);
+}
+
+__device__ __forceinline__ void fsm_bit(Fsm &f, uint32_t b, uint32_t bit_index, int c, uint32_t &nmsg, const TrackOut &out)
+{
+	switch (f.fsm) {
+	case GAIS_ST_DATA:
+		if (f.stuffed) {
+			if (b) f.fsm = GAIS_ST_STOPFLAG;
+			f.stuffed = 0;
+		} else {
+			if (b == f.last && b == 1u) {
+				if (++f.nones == 4u) { f.stuffed = 1; f.nones = 0; }
+			} else {
+				f.nones = 0;
+			}
+			f.store[f.pos >> 5] |= b << (f.pos & 31u);
+			f.pos++;
+			if (f.pos >= 449u)
+				fsm_reset(f);
+		}
+		break;
+	case GAIS_ST_HUNT:
+		f.nalt = (b != f.last) ? f.nalt + 1u : 0u;
+		if (f.nalt > 14u && b == 0u) { f.fsm = GAIS_ST_PREAMBLE; f.nalt = 0; }
+		break;
+	case GAIS_ST_PREAMBLE:
+		if (b != f.last && f.nflag == 0u) {
+			/* antallpreamble++ here is never read before it is zeroed again */
+		} else if (b == 1u) {
+			if (f.nflag == 0u) f.nflag = 3;
+			else if (f.nflag == 5u) { f.nflag = 6; f.nalt = 0; f.fsm = GAIS_ST_STARTFLAG; }
+			else f.nflag++;
+		} else {
+			if (f.nflag == 0u) f.nflag = 1;
+			else fsm_reset(f);
+		}
+		break;
+	case GAIS_ST_STARTFLAG:
+		if (f.nflag >= 7u) {
+			if (b == 0u) {
+				f.fsm = GAIS_ST_DATA; f.nflag = 0; f.nones = 0; f.pos = 0;
+#pragma unroll
+				for (int i = 0; i < GAIS_STORE_WORDS; i++) f.store[i] = 0;
+			} else {
+				fsm_reset(f);
+			}
+		} else if (b == 0u) {
+			fsm_reset(f);
+		}
+		f.nflag++;                                           /* src/protodec.c:1092 */
+		break;
+	default: /* GAIS_ST_STOPFLAG */
+		frame_end(f, b, bit_index, c, nmsg, out);
+		break;
+	}
+	f.last = b;                                                  /* src/protodec.c:1119 */
+}
+
+__global__ void __launch_bounds__(128)
+track_simple_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, int64_t n_frames, TrackOut out)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= n_channels)
+		return;
+
+	ChanState *s = &st[c];
+	uint32_t pll = s->pll, prev = s->prev, lastbit = s->lastbit, n_bits = s->n_bits;
+	Fsm f;
+	f.fsm = s->fsm; f.stuffed = s->stuffed; f.last = s->last; f.nflag = s->nflag; f.nones = s->nones;
+	f.nalt = s->nalt; f.pos = s->pos; f.seqnr = s->seqnr;
+	f.ok = s->ok; f.crcfail = s->crcfail; f.sizefail = s->sizefail;
+	for (int i = 0; i < GAIS_STORE_WORDS; i++) f.store[i] = s->store[i];
+
+	/* message / bit cursors of the RUN continue across its time tiles */
+	uint32_t nmsg = out.run_count[c], run_bits = out.run_bits[c], acc = 0;
+	if (out.bits && (run_bits & 31u))
+		acc = out.bits[(int64_t) c * out.bits_row_words + (run_bits >> 5)];
+	const int64_t n_words = (n_frames + 31) >> 5;
+	for (int64_t w = 0; w < n_words; w++) {
+		uint32_t sw = signs[w * n_channels + c];
+		int nb = (n_frames - w * 32 < 32) ? (int) (n_frames - w * 32) : 32;
+		for (int j = 0; j < nb; j++) {
+			uint32_t cur = (sw >> j) & 1u;
+			if (cur != prev)                                    /* src/receiver.c:113-119 */
+				pll += (pll < 0x8000u) ? GAIS_PLL_NUDGE : (0u - GAIS_PLL_NUDGE);
+			prev = cur;
+			pll += GAIS_PLL_INC;
+			if (pll > 0xffffu) {                                /* src/receiver.c:124-134 */
+				uint32_t b = (cur == lastbit) ? 1u : 0u;
+				lastbit = cur;
+				pll &= 0xffffu;
+				if (out.bits) {
+					acc |= b << (run_bits & 31u);
+					if ((run_bits & 31u) == 31u) {
+						out.bits[(int64_t) c * out.bits_row_words + (run_bits >> 5)] = acc;
+						acc = 0;
+					}
+				}
+				run_bits++;
+				fsm_bit(f, b, n_bits, c, nmsg, out);
+				n_bits++;
+			}
+		}
+	}
+	if (out.bits && (run_bits & 31u))
+		out.bits[(int64_t) c * out.bits_row_words + (run_bits >> 5)] = acc;
+
+	s->pll = pll; s->prev = (uint8_t) prev; s->lastbit = (uint8_t) lastbit; s->n_bits = n_bits;
+	s->fsm = (uint8_t) f.fsm; s->stuffed = (uint8_t) f.stuffed; s->last = (uint8_t) f.last;
+	s->nflag = (uint8_t) f.nflag; s->nones = (uint8_t) f.nones; s->seqnr = (uint8_t) f.seqnr;
+	s->nalt = (uint16_t) f.nalt; s->pos = (uint16_t) f.pos;
+	s->ok = f.ok; s->crcfail = f.crcfail; s->sizefail = f.sizefail;
+	for (int i = 0; i < GAIS_STORE_WORDS; i++) s->store[i] = f.store[i];
+	out.run_count[c] = nmsg;
+	out.run_bits[c] = run_bits;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K4: exclusive scan of per-channel message counts (single block, sequential over chunks of
+ * 1024 -- n_channels <= a few hundred thousand) and gather into the dense array.
+ * ------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(1024)
+scan_counts_kernel(const uint32_t *__restrict__ counts, int n, uint64_t *__restrict__ offsets /* n+1 */)
+{
+	__shared__ uint32_t warp_sums[32];
+	__shared__ uint64_t carry;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (int base = 0; base < n; base += 1024) {
+		int i = base + threadIdx.x;
+		uint32_t v = (i < n) ? counts[i] : 0u, x = v;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+			if (lane >= d) x += y;
+		}
+		if (lane == 31) warp_sums[warp] = x;
+		__syncthreads();
+		if (warp == 0) {
+			uint32_t ws = warp_sums[lane], xs = ws;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				uint32_t y = __shfl_up_sync(0xffffffffu, xs, d);
+				if (lane >= d) xs += y;
+			}
+			warp_sums[lane] = xs - ws;   /* exclusive */
+		}
+		__syncthreads();
+		uint64_t excl = carry + warp_sums[warp] + (x - v);
+		if (i < n) offsets[i] = excl;
+		__syncthreads();
+		if (threadIdx.x == 1023) carry = excl + v;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) offsets[n] = carry;
+}
+
+/* one warp per channel: copy count[c] 64-byte records, 16 B per lane */
+__global__ void gather_msgs_kernel(const gais_msg *__restrict__ slots, int slot_cap, const uint32_t *__restrict__ counts,
+				   const uint64_t *__restrict__ offsets, int n_channels, gais_msg *__restrict__ dense)
+{
+	int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (c >= n_channels)
+		return;
+	uint32_t cnt = counts[c];
+	const uint4 *src = reinterpret_cast<const uint4 *>(slots + (int64_t) c * slot_cap);
+	uint4 *dst = reinterpret_cast<uint4 *>(dense + offsets[c]);
+	for (uint32_t i = lane; i < cnt * 4u; i += 32)
+		dst[i] = src[i];
+}
+
+/* K5: one thread per message */
+__global__ void nmea_kernel(const gais_msg *__restrict__ msgs, int64_t n, gais_nmea_rec *__restrict__ out)
+{
+	int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	gais_msg m = msgs[i];
+	char text[GAIS_NMEA_STRIDE];
+	int len = gn_format(m.payload, m.nbits, m.flags & 15, text);
+	gais_nmea_rec *r = &out[i];
+	r->len = (uint8_t) len;
+	for (int k = 0; k < len; k++)
+		r->text[k] = text[k];
+}
+
+/* sum of counters over channels (3 x int64) */
+__global__ void totals_kernel(const ChanState *__restrict__ st, int n_channels, unsigned long long *totals)
+{
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	long long a = 0, b = 0, d = 0;
+	if (c < n_channels) { a = st[c].ok; b = st[c].crcfail; d = st[c].sizefail; }
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		a += __shfl_down_sync(0xffffffffu, a, o);
+		b += __shfl_down_sync(0xffffffffu, b, o);
+		d += __shfl_down_sync(0xffffffffu, d, o);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		atomicAdd(&totals[0], (unsigned long long) a);
+		atomicAdd(&totals[1], (unsigned long long) b);
+		atomicAdd(&totals[2], (unsigned long long) d);
+	}
+}
+
+} /* namespace gais */
+#endif

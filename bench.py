@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 AIS receive path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU receiver
+
+A step is one pass of the hot path (receiver_run() for every channel of the batch, through
+message compaction) over one batch of synthetic GMSK int16 audio that is already resident in
+HBM.  Workload at N GPUs: 65536 channels x 480000 samples (10 s at 48 kHz) PER GPU -- BASELINE
+config "65536 batched channels ... single B200" at N=1 and "524288 channels sharded across
+8xB200" at N=8 (weak scaling; channels are independent, no data-path collective; the only
+exchange is the NCCL collection of decoded-message buffers on rank 0, inside the timed step).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "Msamples/s demodulated (FIR + DPLL + NRZI + HDLC + CRC-16, AIS msgs/s alongside)"
+UNIT = "Msamples/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--channels", type=int, default=65536, help="channels per GPU")
+    ap.add_argument("--frames", type=int, default=480000, help="samples per channel per step")
+    ap.add_argument("--sigma", type=float, default=300.0)
+    ap.add_argument("--rho", type=float, default=0.5)
+    ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--fir-mode", default="guard", choices=["guard", "exact"])
+    ap.add_argument("--tile-frames", type=int, default=0)
+    ap.add_argument("--e2e-channels", type=int, default=4096)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-channels-per-core", type=int, default=24)
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        except Exception:
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(host_planar, cores: int):
+    """the reference's CPU receiver (oracle/_ref) -- or the port when it was never built -- on a
+    bounded sample of the same workload, one struct receiver per channel, all host threads"""
+    import oracle_lib as O
+
+    kind = "reference" if (ROOT / "oracle" / "_ref" / "libgnuais_ref.so").exists() else "port"
+    chk = O.ref(tap=False, quiet=False) if kind == "reference" else O.port()
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)          # the reference printf()s one line per message (src/protodec.c:934)
+    try:
+        secs, ok = chk.bench(host_planar, cores)
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved); os.close(devnull)
+    n = host_planar.shape[0] * host_planar.shape[1]
+    return {"value": n / secs / 1e6, "unit": UNIT, "cores": cores, "kind": kind, "msgs_per_s": ok / secs,
+            "sample": f"{host_planar.shape[0]} channels x {host_planar.shape[1]} samples of the same workload "
+                      f"({n / 1e6:.1f} Msamples, {secs:.2f} s wall), receiver_run() in 1020-frame chunks"}
+
+
+def reference_arm(args):
+    """--impl reference: the reference's own CPU implementation on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    from gnuais_b200 import SynthParams, synth_host
+
+    cores = os.cpu_count() or 1
+    n_ch = max(cores, min(cores * args.cpu_channels_per_core, 4096))
+    frames = args.frames
+    # bounded sample of OUR arm's workload: its first n_ch channels (same seed -> same audio)
+    t0 = time.time()
+    x = synth_host(SynthParams(seed=args.seed, sigma=args.sigma, rho=args.rho), n_ch, frames)
+    gen_s = time.time() - t0
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = cpu_baseline(x, cores)
+        if i >= args.warmup:
+            vals.append(last)
+    n = n_ch * frames
+    secs = [n / (v["value"] * 1e6) for v in vals]
+    value = n * len(secs) / sum(secs) / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32/u32", "data": "synthetic",
+        "config": {"workload": f"bounded sample: first {n_ch} of the {args.channels} channels/GPU x {frames} samples "
+                               f"(48 kHz int16 synthetic GMSK, seed {args.seed}, sigma {args.sigma}, rho {args.rho}) per step",
+                   "host_gen_s": round(gen_s, 2)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": last["kind"], "sample": last["sample"]},
+        "msgs_per_s": sum(v["msgs_per_s"] for v in vals) / len(vals),
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from gnuais_b200 import BatchReceiver, SynthParams, synth_device
+    from gnuais_b200 import dist as gdist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: gnuais_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_ch, frames = args.channels, args.frames
+    note = ""
+    try:
+        d = torch.empty((n_ch, frames), dtype=torch.int16, device=dev)
+    except torch.cuda.OutOfMemoryError:
+        frames = 96000
+        note = " (480000-sample rows did not fit next to the result buffers: fell back to 96000 samples per step)"
+        d = torch.empty((n_ch, frames), dtype=torch.int16, device=dev)
+    p = SynthParams(seed=args.seed, sigma=args.sigma, rho=args.rho)
+    first_channel = rank * n_ch
+    synth_device(p, d, n_ch, frames, first_channel=first_channel)
+    torch.cuda.synchronize()
+
+    rx = BatchReceiver(n_ch, frames, device=local_rank, fir_mode=args.fir_mode, tile_frames=args.tile_frames)
+    stream = torch.cuda.current_stream(dev)
+    acc = {"fir_ms": 0.0, "track_ms": 0.0, "post_ms": 0.0, "total_ms": 0.0, "launches": 0, "tiles": 0, "msgs": 0,
+           "gather_bytes": 0}
+
+    def step(timed: bool):
+        rx.run(d, stream=stream.cuda_stream)
+        rx.sync()
+        if world > 1:
+            recs = gdist.globalize_channels(gdist.device_records(rx), first_channel)
+            out = gdist.gather_records(recs, dst=0)
+            if timed and out is not None:
+                acc["gather_bytes"] += int(out.numel())
+        if timed:
+            tm = rx.timing()
+            for k in ("fir_ms", "track_ms", "post_ms", "total_ms"):
+                acc[k] += tm[k]
+            acc["launches"] += tm["launches"]
+            acc["msgs"] += rx.message_count()
+
+    for _ in range(max(args.warmup, 0)):
+        step(False)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step(True)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        m = torch.tensor([acc["msgs"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(m, op=dist.ReduceOp.SUM)
+        total_msgs = int(m.item())
+    else:
+        total_msgs = acc["msgs"]
+
+    tile_frames = rx_tile_frames(n_ch, args.tile_frames)
+    n_tiles = (frames + tile_frames - 1) // tile_frames
+    samples_per_step = n_ch * frames * world
+    value = samples_per_step * args.steps / (ms * 1e-3) / 1e6
+    totals = rx.totals()
+
+    # ---- roofline of the dominant kernel (CUDA events inside the library, on the run's stream) ----
+    peak, peak_src = measured_peak()
+    fir_avg = acc["fir_ms"] / (args.steps * n_tiles)
+    trk_avg = acc["track_ms"] / (args.steps * n_tiles)
+    dom = "fir_sign" if fir_avg >= trk_avg else "track"
+    launch_ms = max(fir_avg, trk_avg)
+    samples_per_launch = n_ch * min(tile_frames, frames) if n_tiles > 1 else n_ch * frames
+    msgs_per_launch = acc["msgs"] / (args.steps * n_tiles)
+    # algorithmic bytes: 2 B per input sample for the kernel that reads the audio;
+    # 64 B per emitted record belongs to the tracking kernel
+    alg_bytes = 2.0 * samples_per_launch if dom == "fir_sign" else 2.0 * samples_per_launch + 64.0 * msgs_per_launch
+    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "avg_launch_ms": launch_ms,
+                "alg_bytes_per_launch": alg_bytes,
+                "chain": {"fir_ms_per_step": acc["fir_ms"] / args.steps, "track_ms_per_step": acc["track_ms"] / args.steps,
+                          "post_ms_per_step": acc["post_ms"] / args.steps,
+                          "whole_chain_GBps": (2.0 * n_ch * frames + 64.0 * acc["msgs"] / args.steps)
+                          / (acc["total_ms"] / args.steps * 1e-3) / 1e9}}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32/u32", "data": "synthetic",
+        "config": {"workload": f"{n_ch} batched channels/GPU x {frames} samples (48 kHz int16, {frames / 48000:.0f} s), planar, "
+                               f"synthetic GMSK seed {args.seed} sigma {args.sigma} rho {args.rho}{note}",
+                   "channels_per_gpu": n_ch, "frames_per_channel": frames, "fir_mode": args.fir_mode,
+                   "tile_frames": tile_frames, "parallelism": f"channels sharded x{world}, no data-path collective",
+                   "l2": f"input {2 * n_ch * frames / 1e9:.1f} GB per GPU >> 126 MB L2: no flush needed between steps"},
+        "msgs_per_s": total_msgs / (ms * 1e-3), "msgs_per_step": total_msgs / args.steps,
+        "counters_rank0": {"ok": totals[0], "crcfail": totals[1], "sizefail": totals[2]},
+        "roofline": roofline, "gpu_launches": acc["launches"], "clocks": clocks,
+    }
+    if world > 1:
+        line["gather_bytes_per_step_rank0"] = acc["gather_bytes"] / args.steps
+
+    # ---- end to end through the C-ABI with HOST buffers (H2D + D2H inside the timed region) ----
+    if not args.no_e2e:
+        e_ch = min(args.e2e_channels, n_ch)
+        host = torch.empty((e_ch, frames), dtype=torch.int16, pin_memory=True)
+        host.copy_(d[:e_ch])
+        torch.cuda.synchronize()
+        rx.close()
+        del d
+        torch.cuda.empty_cache()
+        rxe = BatchReceiver(e_ch, frames, device=local_rank, fir_mode=args.fir_mode, tile_frames=args.tile_frames)
+        hv = host.numpy()
+        d2h = 0
+        for i in range(2):
+            rxe.run(hv); rxe.messages()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e_steps = max(3, min(args.steps, 5))
+        for _ in range(e_steps):
+            rxe.run(hv)
+            d2h += rxe.messages().nbytes
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        line["e2e"] = {"value": e_ch * frames * world * e_steps / dt / 1e6, "unit": UNIT,
+                       "h2d_bytes_per_step": 2 * e_ch * frames, "d2h_bytes_per_step": d2h // e_steps,
+                       "workload": f"{e_ch} channels/GPU x {frames} samples from pinned host memory through gais_run_host(), "
+                                   f"message records copied back every step", "steps": e_steps}
+        cpu_src = hv
+        rxe.close()
+    else:
+        cpu_src = None
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_cpu = max(cores, min(cores * args.cpu_channels_per_core, n_ch))
+        if cpu_src is not None and cpu_src.shape[0] >= n_cpu:
+            sample = np.ascontiguousarray(cpu_src[:n_cpu])
+        else:
+            from gnuais_b200 import synth_host
+            sample = synth_host(p, n_cpu, frames, first_channel=first_channel)
+        line["cpu_baseline"] = cpu_baseline(sample, cores)
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def rx_tile_frames(n_ch: int, requested: int) -> int:
+    """mirror of the library's default time-tile choice (gais_api.cu gais_create)"""
+    tile = requested or int(os.environ.get("GAIS_TILE_FRAMES", "0") or 0)
+    if tile <= 0:
+        tile = 32 * 1024 * 1024 * 8 // n_ch
+        tile = max(2048, min(65536, tile))
+    return (tile + 1023) // 1024 * 1024
+
+
+if __name__ == "__main__":
+    sys.exit(main())

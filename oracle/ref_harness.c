@@ -34,6 +34,8 @@
 #include "filter.h"
 #include "protodec.h"
 #include "cfg.h"
+#include "hlog.h"
+#include <syslog.h>
 
 /* ---- taps (only live in the *_tap.so link; harmless otherwise) ------------------------- */
 
@@ -85,6 +87,9 @@ void gref_set_quiet(int quiet)
 {
 	for (int i = 0; i <= MAX_AIS_PACKET_TYPE; i++)
 		skip_type[i] = quiet ? 1 : 0;
+	/* the "Level on ch A too high" notice of src/receiver.c:137-147 is wall-clock gated
+	 * diagnostics on stderr, not a parity output: raise the hlog threshold above it */
+	log_level = quiet ? LOG_ERR : LOG_INFO;
 }
 
 /*

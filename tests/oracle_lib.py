@@ -117,7 +117,9 @@ def ref_available() -> bool:
     return (ORACLE / "_ref" / "libgnuais_ref_tap.so").exists() or Path("/root/reference/src/receiver.c").exists()
 
 
-def ref(tap: bool = True) -> _Checker:
+def ref(tap: bool = True, quiet: bool = True) -> _Checker:
+    """quiet=True (tests): skip_type[] gates the per-message printf + field decoders and hlog is
+    raised to LOG_ERR; quiet=False (CPU baseline): the reference's default behaviour."""
     key = "ref_tap" if tap else "ref"
     if key not in _cache:
         p = ORACLE / "_ref" / ("libgnuais_ref_tap.so" if tap else "libgnuais_ref.so")
@@ -125,6 +127,6 @@ def ref(tap: bool = True) -> _Checker:
             build_oracle(ref=True)
         chk = _Checker(p, "gref", False)
         chk.lib.gref_set_quiet.argtypes = [C.c_int]
-        chk.lib.gref_set_quiet(1)   # no per-message printf in the test process
         _cache[key] = chk
+    _cache[key].lib.gref_set_quiet(1 if quiet else 0)
     return _cache[key]

@@ -651,6 +651,14 @@ extern "C" int gais_get_signs(gais_ctx *ctx, uint32_t *h_words, int64_t cap_word
 	if (words > cap_words)
 		words = cap_words;
 	CK(cudaMemcpy(h_words, ctx->d_signs[0], (size_t) words * 4, cudaMemcpyDeviceToHost));
+	/* the device keeps sign words MSB first; the ABI promises bit j = sample 32w + j */
+	for (int64_t i = 0; i < words; i++) {
+		uint32_t v = h_words[i];
+		v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+		v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+		v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4);
+		h_words[i] = (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24);
+	}
 	return 0;
 }
 

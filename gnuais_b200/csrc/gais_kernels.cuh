@@ -54,30 +54,32 @@ __device__ __forceinline__ float exact_fir(const float *xs /* 36 window values *
 }
 
 __global__ void __launch_bounds__(K1_CH * 32)
-fir_sign_exact_kernel(SampleView in, const ChanState *__restrict__ st, int hist_sel,
-		      int n_channels, int64_t n_frames, uint32_t *__restrict__ signs)
+fir_sign_exact_kernel(SampleView in, const ChanState *__restrict__ st, int hist_sel, int c_begin, int c_end,
+		      int64_t n_begin, int64_t n_end, int n_channels, uint32_t *__restrict__ signs)
 {
+	/* channels [c_begin, c_end), samples [n_begin, n_end) of the tile; n_begin % 32 == 0.
+	 * Sign-word format (device): MSB first, bit (31 - j) of word w = (out[32w + j] > 0). */
 	__shared__ int16_t tile[K1_CH][K1_ROW];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int c = blockIdx.x * K1_CH + warp;
-	const int64_t n0 = (int64_t) blockIdx.y * K1_TILE;
+	const int c = c_begin + blockIdx.x * K1_CH + warp;
+	const int64_t n0 = n_begin + (int64_t) blockIdx.y * K1_TILE;
 
-	if (c < n_channels) {
+	if (c < c_end) {
 		const int16_t *row = in.base + (int64_t) c * in.ch_stride;
 		for (int i = lane; i < K1_TILE + GAIS_NTAPS; i += 32) {
 			int64_t n = n0 - GAIS_NTAPS + i;
 			int16_t v = 0;
 			if (n < 0)
 				v = st[c].hist[hist_sel][GAIS_NTAPS + n];
-			else if (n < n_frames)
+			else if (n < n_end)
 				v = row[n * in.t_stride];
 			tile[warp][i] = v;
 		}
 	}
 	__syncwarp();
-	if (c >= n_channels)
+	if (c >= c_end)
 		return;
-	if (n0 + 32 * lane >= n_frames)
+	if (n0 + 32 * lane >= n_end)
 		return;
 
 	float xs[GAIS_NTAPS + 31];
@@ -89,9 +91,9 @@ fir_sign_exact_kernel(SampleView in, const ChanState *__restrict__ st, int hist_
 #pragma unroll
 	for (int j = 0; j < 32; j++) {
 		float s = exact_fir(&xs[j]);
-		word |= (s > 0.0f ? 1u : 0u) << j;
+		word |= (s > 0.0f ? 1u : 0u) << (31 - j);
 	}
-	signs[((int64_t) blockIdx.y * 32 + lane) * n_channels + c] = word;
+	signs[(n0 / 32 + lane) * n_channels + c] = word;
 }
 
 /* next run's history = last 36 samples seen (src/filter.c:129-134 keeps exactly these) */
@@ -271,7 +273,7 @@ track_simple_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_cha
 		uint32_t sw = signs[w * n_channels + c];
 		int nb = (n_frames - w * 32 < 32) ? (int) (n_frames - w * 32) : 32;
 		for (int j = 0; j < nb; j++) {
-			uint32_t cur = (sw >> j) & 1u;
+			uint32_t cur = (sw >> (31 - j)) & 1u;   /* MSB-first sign words */
 			if (cur != prev)                                    /* src/receiver.c:113-119 */
 				pll += (pll < 0x8000u) ? GAIS_PLL_NUDGE : (0u - GAIS_PLL_NUDGE);
 			prev = cur;

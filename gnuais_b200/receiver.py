@@ -95,7 +95,9 @@ class BatchReceiver:
                 n_frames = samples.shape[1] if planar else samples.shape[0]
             if stride is None:
                 stride = samples.stride(0)
-                assert samples.stride(1) == 1
+                assert samples.stride(1) == 1 or samples.shape[1] == 1
+                if samples.shape[0] == 1:      # the stride of a length-1 axis is arbitrary
+                    stride = samples.shape[1]
             if stream is None:
                 stream = torch.cuda.current_stream(samples.device).cuda_stream
             self._keepalive = samples
@@ -105,11 +107,11 @@ class BatchReceiver:
         if _is_torch(samples):
             samples = samples.numpy()
         a = np.asarray(samples)
-        assert a.dtype == np.int16 and a.ndim == 2 and a.strides[1] == 2
+        assert a.dtype == np.int16 and a.ndim == 2 and (a.strides[1] == 2 or a.shape[1] == 1)
         if n_frames is None:
             n_frames = a.shape[1] if planar else a.shape[0]
         if stride is None:
-            stride = a.strides[0] // 2
+            stride = a.shape[1] if a.shape[0] == 1 else a.strides[0] // 2
         self._keepalive = a
         L.check(self._lib.gais_run_host(self._ctx, a.ctypes.data_as(C.c_void_p), n_frames, stride))
 

@@ -286,6 +286,31 @@ static int ensure_tile_events(gais_ctx *ctx, int n_tiles)
 	return 0;
 }
 
+static TrackOut make_out(gais_ctx *ctx)
+{
+	TrackOut out;
+	out.slots = ctx->d_slots;
+	out.run_count = ctx->d_run_count;
+	out.bits = ctx->d_bits;
+	out.run_bits = ctx->d_run_bits;
+	out.slot_cap = ctx->slot_cap;
+	out.bits_row_words = ctx->bits_row_words;
+	out.overflow = ctx->d_overflow;
+	return out;
+}
+
+/* after the last tile: frame check (CRC, counters, seqnr, compaction) and the count scan */
+static int enqueue_post(gais_ctx *ctx, cudaStream_t st)
+{
+	int nl = finalize_launch(ctx->d_state, ctx->n_ch, make_out(ctx), st);
+	if (nl < 0)
+		return fail(GAIS_ECUDA, "frame-check launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+	ctx->launches += nl;
+	scan_counts_kernel<<<1, 1024, 0, st>>>(ctx->d_run_count, ctx->n_ch, ctx->d_offsets);
+	ctx->launches++;
+	return 0;
+}
+
 /* enqueue FIR + tracking for one time tile whose samples are at `view` (n = 0 is the first
  * sample of the tile) */
 static int enqueue_tile(gais_ctx *ctx, SampleView view, int64_t n_frames, int tile_idx, int64_t word_ofs, cudaStream_t st,
@@ -307,14 +332,7 @@ static int enqueue_tile(gais_ctx *ctx, SampleView view, int64_t n_frames, int ti
 	ctx->hist_sel ^= 1;
 	if (timed) CK(cudaEventRecord(ctx->ev_tile[3 * tile_idx + 1], st));
 
-	TrackOut out;
-	out.slots = ctx->d_slots;
-	out.run_count = ctx->d_run_count;
-	out.bits = ctx->d_bits;
-	out.run_bits = ctx->d_run_bits;
-	out.slot_cap = ctx->slot_cap;
-	out.bits_row_words = ctx->bits_row_words;
-	out.overflow = ctx->d_overflow;
+	TrackOut out = make_out(ctx);
 	nl = track_launch(signs, ctx->d_state, ctx->n_ch, n_frames, out, st);
 	if (nl < 0)
 		return fail(GAIS_ECUDA, "tracking launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -335,6 +353,8 @@ static int begin_run(gais_ctx *ctx, int64_t n_frames, cudaStream_t st)
 	ctx->last_frames = n_frames;
 	CK(cudaMemsetAsync(ctx->d_run_count, 0, sizeof(uint32_t) * ctx->n_ch, st));
 	CK(cudaMemsetAsync(ctx->d_run_bits, 0, sizeof(uint32_t) * ctx->n_ch, st));
+	if (ctx->d_bits)
+		CK(cudaMemsetAsync(ctx->d_bits, 0, (size_t) ctx->n_ch * ctx->bits_row_words * 4, st));
 	return 0;
 }
 
@@ -364,8 +384,8 @@ extern "C" int gais_run_device(gais_ctx *ctx, const int16_t *d_samples, int64_t 
 		if ((rc = enqueue_tile(ctx, v, nf, t, f0 / 32, st, true)) != 0)
 			return rc;
 	}
-	scan_counts_kernel<<<1, 1024, 0, st>>>(ctx->d_run_count, ctx->n_ch, ctx->d_offsets);
-	ctx->launches++;
+	if ((rc = enqueue_post(ctx, st)) != 0)
+		return rc;
 	CK(cudaEventRecord(ctx->ev[EV_END], st));
 	CK(cudaGetLastError());
 	ctx->last_stream = st;
@@ -427,8 +447,8 @@ extern "C" int gais_run_host(gais_ctx *ctx, const int16_t *h_samples, int64_t n_
 			return rc;
 		CK(cudaEventRecord(ctx->ev_free[b], st));
 	}
-	scan_counts_kernel<<<1, 1024, 0, st>>>(ctx->d_run_count, ctx->n_ch, ctx->d_offsets);
-	ctx->launches++;
+	if ((rc = enqueue_post(ctx, st)) != 0)
+		return rc;
 	CK(cudaEventRecord(ctx->ev[EV_END], st));
 	CK(cudaGetLastError());
 	ctx->last_stream = st;

@@ -40,12 +40,12 @@ namespace gais {
 constexpr int F_CH = 64;
 constexpr int F_T = 256;
 constexpr int F_HALO = 40;
-constexpr int F_SEG_BYTES = (F_T + F_HALO) * 2;     /* 592 */
-constexpr int F_ROW_BYTES = 656;                    /* 592 padded to 16 (mod 128) */
-constexpr int F_STAGE_BYTES = F_CH * F_ROW_BYTES;   /* 41984 */
-constexpr int F_NSTAGE = 2;
-constexpr int F_THREADS = 256;
-constexpr int F_STAGES_PER_BLOCK = 16;              /* 4096 samples of 64 channels per CTA */
+constexpr int F_ROW_BYTES = (F_T + F_HALO) * 2;     /* 592 = 80 (mod 128): 8 consecutive rows start in 8 different 16-byte bank groups */
+constexpr int F_STAGE_BYTES = F_CH * F_ROW_BYTES;   /* 37888 */
+constexpr int F_NSTAGE = 3;
+constexpr int F_CWARPS = 8;                         /* consumer warps = word columns of a stage */
+constexpr int F_THREADS = (F_CWARPS + 1) * 32;      /* + one producer warp */
+constexpr int F_STAGES_PER_BLOCK = 8;               /* 2048 samples of 64 channels per CTA */
 #define F_E1 0.5f
 #define F_E2 0.25f
 
@@ -98,17 +98,10 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c)
 	return d;
 }
 
-/* ---- tiers 2 and 3 for one doubtful sample; w36 -> x[n-36] inside a shared-memory row --- */
-__device__ __noinline__ bool fir_sign_resolve(const int16_t *w36)
+/* ---- tier 3 for one doubtful sample; w36 -> x[n-36] inside a shared-memory row ----------- */
+__device__ __noinline__ bool fir_sign_exact(const int16_t *w36)
 {
-	/* tier 2: taps 12..23, plain FMAs */
-	float a = 0.0f;
-#pragma unroll
-	for (int i = 12; i <= 23; i++)
-		a = fmaf((float) w36[i], c_taps[i], a);
-	if (fabsf(a) > F_E2)
-		return a > 0.0f;
-	/* tier 3: the reference's own arithmetic.  An all-zero window gives exactly +0 (not > 0). */
+	/* the reference's own arithmetic.  An all-zero window gives exactly +0 (not > 0). */
 	int any = 0;
 	for (int i = 2; i < GAIS_NTAPS - 2; i++)
 		any |= w36[i];
@@ -123,138 +116,159 @@ __device__ __noinline__ bool fir_sign_resolve(const int16_t *w36)
 __device__ __forceinline__ float s16lo(uint32_t v) { return (float) (short) (v & 0xffffu); }
 __device__ __forceinline__ float s16hi(uint32_t v) { return (float) (short) (v >> 16); }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+/* 8 samples of rows A and B -> 8 packed (A, B) float pairs */
+__device__ __forceinline__ void fir_load_chunk(uint64_t *xs, const uint8_t *rowA, const uint8_t *rowB, int byte_ofs)
+{
+	const uint4 a = *reinterpret_cast<const uint4 *>(rowA + byte_ofs);
+	const uint4 b = *reinterpret_cast<const uint4 *>(rowB + byte_ofs);
+	xs[0] = pack2(s16lo(a.x), s16lo(b.x));
+	xs[1] = pack2(s16hi(a.x), s16hi(b.x));
+	xs[2] = pack2(s16lo(a.y), s16lo(b.y));
+	xs[3] = pack2(s16hi(a.y), s16hi(b.y));
+	xs[4] = pack2(s16lo(a.z), s16lo(b.z));
+	xs[5] = pack2(s16hi(a.z), s16hi(b.z));
+	xs[6] = pack2(s16lo(a.w), s16lo(b.w));
+	xs[7] = pack2(s16hi(a.w), s16hi(b.w));
+}
+
 __global__ void __launch_bounds__(F_THREADS, 2)
 fir_sign_fast_kernel(const int16_t *__restrict__ base, int64_t ch_stride, const ChanState *__restrict__ st, int hist_sel,
 		     int n_channels, int n_stages, uint32_t *__restrict__ signs)
 {
 	extern __shared__ __align__(128) uint8_t tile[];
-	__shared__ __align__(8) uint64_t full_bar[F_NSTAGE];
+	__shared__ __align__(8) uint64_t full_bar[F_NSTAGE], empty_bar[F_NSTAGE];
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int cg = blockIdx.x * F_CH;
 	const int s_begin = blockIdx.y * F_STAGES_PER_BLOCK;
 	const int s_end = min(s_begin + F_STAGES_PER_BLOCK, n_stages);
-	const int16_t *gbase = base + (int64_t) cg * ch_stride;
 
 	if (tid == 0) {
-		for (int i = 0; i < F_NSTAGE; i++)
+		for (int i = 0; i < F_NSTAGE; i++) {
 			mbar_init(&full_bar[i], 1);
+			mbar_init(&empty_bar[i], F_CWARPS);
+		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
 
-	/* warp 0 issues the 64 row copies of a stage: lane l brings rows l and l+32 */
-	auto issue = [&](int s) {
-		const int buf = (s - s_begin) & 1;
-		uint8_t *dst = tile + buf * F_STAGE_BYTES;
-		const int64_t n0 = (int64_t) s * F_T;
-		if (lane == 0)
-			mbar_expect_tx(&full_bar[buf], (uint32_t) (F_CH * (s == 0 ? F_T * 2 : F_SEG_BYTES)));
-		__syncwarp();
+	if (warp == F_CWARPS) {
+		/* ===== producer warp: lane l brings rows l and l+32 of every stage ===== */
+		const int16_t *gbase = base + (int64_t) cg * ch_stride;
+		for (int s = s_begin; s < s_end; s++) {
+			const int it = s - s_begin, buf = it % F_NSTAGE;
+			if (it >= F_NSTAGE)
+				mbar_wait(&empty_bar[buf], (uint32_t) ((it / F_NSTAGE - 1) & 1));
+			uint8_t *dst = tile + buf * F_STAGE_BYTES;
+			const int64_t n0 = (int64_t) s * F_T;
+			if (s == 0) {
+				/* no samples before the run: rows start with 4 zeros + the 36 carried samples
+				 * (generic stores; made visible to the consumers by the release of the arrive below) */
+				for (int i = lane; i < F_CH * F_HALO; i += 32) {
+					const int r = i / F_HALO, k = i % F_HALO;
+					const int16_t v = (k < F_HALO - GAIS_NTAPS) ? (int16_t) 0 : st[cg + r].hist[hist_sel][k - (F_HALO - GAIS_NTAPS)];
+					*reinterpret_cast<int16_t *>(dst + r * F_ROW_BYTES + k * 2) = v;
+				}
+			}
+			__syncwarp();
+			if (lane == 0)
+				mbar_expect_tx(&full_bar[buf], (uint32_t) (F_CH * (s == 0 ? F_T * 2 : F_ROW_BYTES)));
+			__syncwarp();
 #pragma unroll
-		for (int h = 0; h < 2; h++) {
-			const int r = lane + 32 * h;
-			const int16_t *src = gbase + (int64_t) r * ch_stride + n0;
-			if (s == 0)   /* no samples before the run: history comes from ChanState */
-				bulk_g2s(dst + r * F_ROW_BYTES + F_HALO * 2, src, F_T * 2, &full_bar[buf]);
-			else
-				bulk_g2s(dst + r * F_ROW_BYTES, src - F_HALO, F_SEG_BYTES, &full_bar[buf]);
+			for (int h = 0; h < 2; h++) {
+				const int r = lane + 32 * h;
+				const int16_t *src = gbase + (int64_t) r * ch_stride + n0;
+				if (s == 0)
+					bulk_g2s(dst + r * F_ROW_BYTES + F_HALO * 2, src, F_T * 2, &full_bar[buf]);
+				else
+					bulk_g2s(dst + r * F_ROW_BYTES, src - F_HALO, F_ROW_BYTES, &full_bar[buf]);
+			}
 		}
-	};
-
-	if (warp == 0) {
-		issue(s_begin);
-		if (s_begin + 1 < s_end)
-			issue(s_begin + 1);
-	}
-	if (s_begin == 0) {
-		/* history rows of stage 0: idx 0..3 zero, idx 4..39 = x[-36..-1] (generic-proxy stores to
-		 * bytes the bulk copy does not touch) */
-		for (int i = tid; i < F_CH * F_HALO; i += F_THREADS) {
-			const int r = i / F_HALO, k = i % F_HALO;
-			int16_t v = (k < F_HALO - GAIS_NTAPS) ? (int16_t) 0 : st[cg + r].hist[hist_sel][k - (F_HALO - GAIS_NTAPS)];
-			*reinterpret_cast<int16_t *>(tile + r * F_ROW_BYTES + k * 2) = v;
-		}
-		__syncthreads();
+		return;
 	}
 
-	/* the 10 centre taps 13..22 (symmetric), each replicated into both halves */
-	uint64_t T[5];
+	/* ===== consumer warps: warp w owns word column w; lane l channels l and l+32 ===== */
+	uint64_t T[6];      /* taps 12..17 (= 23..18), each in both halves */
 #pragma unroll
-	for (int k = 0; k < 5; k++)
-		T[k] = pack2(c_taps[13 + k], c_taps[13 + k]);
+	for (int k = 0; k < 6; k++)
+		T[k] = pack2(c_taps[12 + k], c_taps[12 + k]);
 
 	for (int s = s_begin; s < s_end; s++) {
-		const int it = s - s_begin, buf = it & 1;
-		mbar_wait(&full_bar[buf], (uint32_t) ((it >> 1) & 1));
+		const int it = s - s_begin, buf = it % F_NSTAGE;
+		mbar_wait(&full_bar[buf], (uint32_t) ((it / F_NSTAGE) & 1));
 		const uint8_t *stage = tile + buf * F_STAGE_BYTES;
 		const uint8_t *rowA = stage + lane * F_ROW_BYTES;
 		const uint8_t *rowB = stage + (lane + 32) * F_ROW_BYTES;
-		const int col0 = 32 * warp + 16;          /* first row index loaded by this warp */
+		const int col0 = 32 * warp + 16;      /* row index of xs[0]; output j uses xs[j+1 .. j+10] */
 
-		/* 48 samples of each row, idx col0 .. col0+47; output j uses idx col0 + j + 1 .. + 10 */
 		uint64_t xs[48];
-#pragma unroll
-		for (int q = 0; q < 6; q++) {
-			const uint4 a = *reinterpret_cast<const uint4 *>(rowA + (col0 + 8 * q) * 2);
-			const uint4 b = *reinterpret_cast<const uint4 *>(rowB + (col0 + 8 * q) * 2);
-			xs[8 * q + 0] = pack2(s16lo(a.x), s16lo(b.x));
-			xs[8 * q + 1] = pack2(s16hi(a.x), s16hi(b.x));
-			xs[8 * q + 2] = pack2(s16lo(a.y), s16lo(b.y));
-			xs[8 * q + 3] = pack2(s16hi(a.y), s16hi(b.y));
-			xs[8 * q + 4] = pack2(s16lo(a.z), s16lo(b.z));
-			xs[8 * q + 5] = pack2(s16hi(a.z), s16hi(b.z));
-			xs[8 * q + 6] = pack2(s16lo(a.w), s16lo(b.w));
-			xs[8 * q + 7] = pack2(s16hi(a.w), s16hi(b.w));
-		}
+		fir_load_chunk(xs + 0, rowA, rowB, (col0 + 0) * 2);
+		fir_load_chunk(xs + 8, rowA, rowB, (col0 + 8) * 2);
 
-		uint32_t wordA = 0, wordB = 0;   /* sign bits (1 = negative), first sample ends at the MSB */
+		uint32_t wordA = 0, wordB = 0;        /* sign bits (1 = negative), first sample ends at the MSB */
 #pragma unroll
 		for (int g = 0; g < 4; g++) {
-			float ya[8], yb[8];
+			fir_load_chunk(xs + 8 * g + 16, rowA, rowB, (col0 + 8 * g + 16) * 2);
+			uint64_t acc[8];
 			float m = 3.0e38f;
 #pragma unroll
 			for (int jj = 0; jj < 8; jj++) {
 				const int j = 8 * g + jj;
-				uint64_t acc = fmul2(T[0], xs[j + 1]);
-				acc = ffma2(T[1], xs[j + 2], acc);
-				acc = ffma2(T[2], xs[j + 3], acc);
-				acc = ffma2(T[3], xs[j + 4], acc);
-				acc = ffma2(T[4], xs[j + 5], acc);
-				acc = ffma2(T[4], xs[j + 6], acc);
-				acc = ffma2(T[3], xs[j + 7], acc);
-				acc = ffma2(T[2], xs[j + 8], acc);
-				acc = ffma2(T[1], xs[j + 9], acc);
-				acc = ffma2(T[0], xs[j + 10], acc);
-				unpack2(acc, ya[jj], yb[jj]);
-				m = fminf(m, fminf(fabsf(ya[jj]), fabsf(yb[jj])));
-				wordA = __funnelshift_l(__float_as_uint(ya[jj]), wordA, 1);
-				wordB = __funnelshift_l(__float_as_uint(yb[jj]), wordB, 1);
+				uint64_t a = fmul2(T[1], xs[j + 1]);
+				a = ffma2(T[2], xs[j + 2], a);
+				a = ffma2(T[3], xs[j + 3], a);
+				a = ffma2(T[4], xs[j + 4], a);
+				a = ffma2(T[5], xs[j + 5], a);
+				a = ffma2(T[5], xs[j + 6], a);
+				a = ffma2(T[4], xs[j + 7], a);
+				a = ffma2(T[3], xs[j + 8], a);
+				a = ffma2(T[2], xs[j + 9], a);
+				a = ffma2(T[1], xs[j + 10], a);
+				acc[jj] = a;
+				float ya, yb;
+				unpack2(a, ya, yb);
+				m = fminf(m, fminf(fabsf(ya), fabsf(yb)));
+				wordA = __funnelshift_l(__float_as_uint(ya), wordA, 1);
+				wordB = __funnelshift_l(__float_as_uint(yb), wordB, 1);
 			}
 			if (m <= F_E1) {
-				/* some of these 16 signs are in doubt: settle exactly those */
+				/* some of these 16 signs are in doubt.  Tier 2: add taps 12 and 23 to the sums we
+				 * already hold; tier 3 (the exact chain) only where that is still not decisive */
 #pragma unroll
 				for (int jj = 0; jj < 8; jj++) {
 					const int j = 8 * g + jj;
-					/* x[n-36] of output j sits at row index 32*warp + j + 4 */
-					if (fabsf(ya[jj]) <= F_E1) {
-						bool pos = fir_sign_resolve(reinterpret_cast<const int16_t *>(rowA) + 32 * warp + j + 4);
-						wordA = (wordA & ~(1u << (7 - jj))) | ((pos ? 0u : 1u) << (7 - jj));
-					}
-					if (fabsf(yb[jj]) <= F_E1) {
-						bool pos = fir_sign_resolve(reinterpret_cast<const int16_t *>(rowB) + 32 * warp + j + 4);
-						wordB = (wordB & ~(1u << (7 - jj))) | ((pos ? 0u : 1u) << (7 - jj));
+					float ya, yb;
+					unpack2(acc[jj], ya, yb);
+					if (fabsf(ya) <= F_E1 || fabsf(yb) <= F_E1) {
+						float za, zb;
+						unpack2(ffma2(T[0], xs[j + 11], ffma2(T[0], xs[j], acc[jj])), za, zb);
+						if (fabsf(ya) <= F_E1) {
+							bool neg = za < 0.0f;
+							if (fabsf(za) <= F_E2)
+								neg = !fir_sign_exact(reinterpret_cast<const int16_t *>(rowA) + 32 * warp + j + 4);
+							wordA = (wordA & ~(1u << (7 - jj))) | ((neg ? 1u : 0u) << (7 - jj));
+						}
+						if (fabsf(yb) <= F_E1) {
+							bool neg = zb < 0.0f;
+							if (fabsf(zb) <= F_E2)
+								neg = !fir_sign_exact(reinterpret_cast<const int16_t *>(rowB) + 32 * warp + j + 4);
+							wordB = (wordB & ~(1u << (7 - jj))) | ((neg ? 1u : 0u) << (7 - jj));
+						}
 					}
 				}
 			}
 		}
+		__syncwarp();
+		if (lane == 0)
+			mbar_arrive(&empty_bar[buf]);     /* this warp is done with the buffer */
 		const int64_t wrow = (int64_t) s * (F_T / 32) + warp;
 		signs[wrow * n_channels + cg + lane] = ~wordA;
 		signs[wrow * n_channels + cg + lane + 32] = ~wordB;
-
-		__syncthreads();   /* everyone is done reading this buffer */
-		if (warp == 0 && s + 2 < s_end)
-			issue(s + 2);
 	}
 }
 

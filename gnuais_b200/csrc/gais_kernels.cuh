@@ -3,7 +3,8 @@
  *
  *   fir_sign_kernel   K1  int16 -> 36-tap FIR -> sign bit per sample (32 samples / word)
  *   save_hist_kernel      carries the last 36 samples of the run into the next one
- *   track_kernel      K2+K3  zero-crossing DPLL, slicer, NRZI, HDLC FSM, CRC-16, records
+ *   track_kernel      K2+K3  zero-crossing DPLL, slicer, NRZI, HDLC FSM (gais_track.cuh)
+ *   crc/finalize          CRC-16, counters, seqnr, records (gais_track.cuh)
  *   scan/gather       K4  dense (channel, end_bit)-ordered message array
  *   nmea_kernel       K5  !AIVDM armouring on the GPU
  *
@@ -123,190 +124,6 @@ struct TrackOut {
 	int32_t bits_row_words;
 	int32_t *overflow;        /* set to 1 if a channel ran out of slots */
 };
-
-struct Fsm {
-	uint32_t fsm, stuffed, last, nflag, nones, nalt, pos, seqnr;
-	uint32_t store[GAIS_STORE_WORDS];
-	int32_t ok, crcfail, sizefail;
-};
-
-__device__ __forceinline__ void fsm_reset(Fsm &f)   /* src/protodec.c:87-100 */
-{
-	f.fsm = GAIS_ST_HUNT;
-	f.nflag = 0; f.nalt = 0; f.nones = 0; f.last = 0; f.stuffed = 0; f.pos = 0;
-}
-
-__device__ __forceinline__ uint32_t crc16_x25_bytes(const uint32_t *store, int nbytes)
-{
-	/* bitwise, LSB first, init 0xffff, poly 0x8408; returns ~crc (src/protodec.c:106-118) */
-	uint32_t crc = 0xffffu;
-	for (int k = 0; k < nbytes * 8; k++) {
-		uint32_t bit = (store[k >> 5] >> (k & 31)) & 1u;
-		crc = ((crc ^ bit) & 1u) ? (crc >> 1) ^ 0x8408u : crc >> 1;
-	}
-	return (~crc) & 0xffffu;
-}
-
-__device__ __noinline__ void frame_end(Fsm &f, uint32_t b, uint32_t bit_index, int c, uint32_t &nmsg, const TrackOut &out)
-{
-	int nbits = (int) f.pos - 22;                         /* src/protodec.c:1096 */
-	if (b == 0 && nbits > 0) {
-		int nb = nbits >> 3;
-		if (crc16_x25_bytes(f.store, nb + 2) == 0x0f47u) { /* src/protodec.c:146,166 */
-			f.ok++;
-			if (nmsg < (uint32_t) out.slot_cap) {
-				uint32_t *w = reinterpret_cast<uint32_t *>(&out.slots[(int64_t) c * out.slot_cap + nmsg]);
-				uint32_t type = (f.store[0] & 0xffu) >> 2;
-				uint32_t gate = (type >= 1 && type <= 24) ? 1u : 0u;
-				uint32_t flags = f.seqnr | (gate << 4);
-#pragma unroll
-				for (int i = 0; i < 13; i++) {
-					int lo = 32 * i;
-					uint32_t v = f.store[i];
-					/* keep only the nb payload bytes */
-					if (8 * nb <= lo) v = 0;
-					else if (8 * nb < lo + 32) v &= (1u << (8 * nb - lo)) - 1u;
-					w[i] = v;
-				}
-				{
-					uint32_t v = (nb > 52) ? (f.store[13] & 0xffu) : 0u;   /* payload[52] */
-					w[13] = v | (flags << 8) | ((uint32_t) nbits << 16);
-				}
-				w[14] = (uint32_t) c;
-				w[15] = bit_index;
-				if (gate)
-					f.seqnr = (f.seqnr + 1u) % 10u;               /* src/protodec.c:924-926 */
-				nmsg++;
-			} else {
-				/* still advance seqnr so later records stay right; flag the overflow */
-				uint32_t type = (f.store[0] & 0xffu) >> 2;
-				if (type >= 1 && type <= 24)
-					f.seqnr = (f.seqnr + 1u) % 10u;
-				*out.overflow = 1;
-			}
-		} else {
-			f.crcfail++;
-		}
-	} else {
-		f.sizefail++;
-	}
-	fsm_reset(f);
-}
-
-__device__ __forceinline__ void fsm_bit(Fsm &f, uint32_t b, uint32_t bit_index, int c, uint32_t &nmsg, const TrackOut &out)
-{
-	switch (f.fsm) {
-	case GAIS_ST_DATA:
-		if (f.stuffed) {
-			if (b) f.fsm = GAIS_ST_STOPFLAG;
-			f.stuffed = 0;
-		} else {
-			if (b == f.last && b == 1u) {
-				if (++f.nones == 4u) { f.stuffed = 1; f.nones = 0; }
-			} else {
-				f.nones = 0;
-			}
-			f.store[f.pos >> 5] |= b << (f.pos & 31u);
-			f.pos++;
-			if (f.pos >= 449u)
-				fsm_reset(f);
-		}
-		break;
-	case GAIS_ST_HUNT:
-		f.nalt = (b != f.last) ? f.nalt + 1u : 0u;
-		if (f.nalt > 14u && b == 0u) { f.fsm = GAIS_ST_PREAMBLE; f.nalt = 0; }
-		break;
-	case GAIS_ST_PREAMBLE:
-		if (b != f.last && f.nflag == 0u) {
-			/* antallpreamble++ here is never read before it is zeroed again */
-		} else if (b == 1u) {
-			if (f.nflag == 0u) f.nflag = 3;
-			else if (f.nflag == 5u) { f.nflag = 6; f.nalt = 0; f.fsm = GAIS_ST_STARTFLAG; }
-			else f.nflag++;
-		} else {
-			if (f.nflag == 0u) f.nflag = 1;
-			else fsm_reset(f);
-		}
-		break;
-	case GAIS_ST_STARTFLAG:
-		if (f.nflag >= 7u) {
-			if (b == 0u) {
-				f.fsm = GAIS_ST_DATA; f.nflag = 0; f.nones = 0; f.pos = 0;
-#pragma unroll
-				for (int i = 0; i < GAIS_STORE_WORDS; i++) f.store[i] = 0;
-			} else {
-				fsm_reset(f);
-			}
-		} else if (b == 0u) {
-			fsm_reset(f);
-		}
-		f.nflag++;                                           /* src/protodec.c:1092 */
-		break;
-	default: /* GAIS_ST_STOPFLAG */
-		frame_end(f, b, bit_index, c, nmsg, out);
-		break;
-	}
-	f.last = b;                                                  /* src/protodec.c:1119 */
-}
-
-__global__ void __launch_bounds__(128)
-track_simple_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, int64_t n_frames, TrackOut out)
-{
-	const int c = blockIdx.x * blockDim.x + threadIdx.x;
-	if (c >= n_channels)
-		return;
-
-	ChanState *s = &st[c];
-	uint32_t pll = s->pll, prev = s->prev, lastbit = s->lastbit, n_bits = s->n_bits;
-	Fsm f;
-	f.fsm = s->fsm; f.stuffed = s->stuffed; f.last = s->last; f.nflag = s->nflag; f.nones = s->nones;
-	f.nalt = s->nalt; f.pos = s->pos; f.seqnr = s->seqnr;
-	f.ok = s->ok; f.crcfail = s->crcfail; f.sizefail = s->sizefail;
-	for (int i = 0; i < GAIS_STORE_WORDS; i++) f.store[i] = s->store[i];
-
-	/* message / bit cursors of the RUN continue across its time tiles */
-	uint32_t nmsg = out.run_count[c], run_bits = out.run_bits[c], acc = 0;
-	if (out.bits && (run_bits & 31u))
-		acc = out.bits[(int64_t) c * out.bits_row_words + (run_bits >> 5)];
-	const int64_t n_words = (n_frames + 31) >> 5;
-	for (int64_t w = 0; w < n_words; w++) {
-		uint32_t sw = signs[w * n_channels + c];
-		int nb = (n_frames - w * 32 < 32) ? (int) (n_frames - w * 32) : 32;
-		for (int j = 0; j < nb; j++) {
-			uint32_t cur = (sw >> (31 - j)) & 1u;   /* MSB-first sign words */
-			if (cur != prev)                                    /* src/receiver.c:113-119 */
-				pll += (pll < 0x8000u) ? GAIS_PLL_NUDGE : (0u - GAIS_PLL_NUDGE);
-			prev = cur;
-			pll += GAIS_PLL_INC;
-			if (pll > 0xffffu) {                                /* src/receiver.c:124-134 */
-				uint32_t b = (cur == lastbit) ? 1u : 0u;
-				lastbit = cur;
-				pll &= 0xffffu;
-				if (out.bits) {
-					acc |= b << (run_bits & 31u);
-					if ((run_bits & 31u) == 31u) {
-						out.bits[(int64_t) c * out.bits_row_words + (run_bits >> 5)] = acc;
-						acc = 0;
-					}
-				}
-				run_bits++;
-				fsm_bit(f, b, n_bits, c, nmsg, out);
-				n_bits++;
-			}
-		}
-	}
-	if (out.bits && (run_bits & 31u))
-		out.bits[(int64_t) c * out.bits_row_words + (run_bits >> 5)] = acc;
-
-	s->pll = pll; s->prev = (uint8_t) prev; s->lastbit = (uint8_t) lastbit; s->n_bits = n_bits;
-	s->fsm = (uint8_t) f.fsm; s->stuffed = (uint8_t) f.stuffed; s->last = (uint8_t) f.last;
-	s->nflag = (uint8_t) f.nflag; s->nones = (uint8_t) f.nones; s->seqnr = (uint8_t) f.seqnr;
-	s->nalt = (uint16_t) f.nalt; s->pos = (uint16_t) f.pos;
-	s->ok = f.ok; s->crcfail = f.crcfail; s->sizefail = f.sizefail;
-	for (int i = 0; i < GAIS_STORE_WORDS; i++) s->store[i] = f.store[i];
-	out.run_count[c] = nmsg;
-	out.run_bits[c] = run_bits;
-}
 
 /* ------------------------------------------------------------------------------------------
  * K4: exclusive scan of per-channel message counts (single block, sequential over chunks of

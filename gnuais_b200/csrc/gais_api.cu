@@ -119,7 +119,7 @@ extern "C" int gais_reset(gais_ctx *ctx)
 	CK(cudaDeviceSynchronize());
 	ChanState init;
 	memset(&init, 0, sizeof(init));
-	init.fsm = GAIS_ST_HUNT;   /* protodec_reset(); everything else is 0 (src/protodec.c:54-100, src/receiver.c:52-74) */
+	init.fsm = (uint8_t) hdlc_hunt_id(0, 0, 0);   /* protodec_reset(); everything else is 0 (src/protodec.c:54-100, src/receiver.c:52-74) */
 	/* replicate by doubling copies */
 	CK(cudaMemcpy(ctx->d_state, &init, sizeof(init), cudaMemcpyHostToDevice));
 	for (int64_t have = 1; have < ctx->n_ch; have *= 2) {
@@ -208,9 +208,11 @@ extern "C" int gais_create(const gais_config *cfg, gais_ctx **out)
 	if (cfg->reserved[1] > 0)
 		tile = cfg->reserved[1];
 	if (tile <= 0) {
-		/* default: keep one tile of sign words (n_ch * tile / 8 bytes) around 32 MB so it
-		 * lives in the 126 MB L2 between the FIR and the tracking kernel */
-		tile = (int64_t) 32 * 1024 * 1024 * 8 / ctx->n_ch;
+		/* default: 256 MB of sign words per tile (n_ch * tile / 8 bytes).  Measured on B200
+		 * (profiles/r1_sweep_tiles.txt): fewer, longer launches beat keeping the sign words inside
+		 * the 126 MB L2 -- the extra 1/16 byte per sample of HBM traffic is cheaper than the
+		 * per-launch ramp of 2 x 117 kernels */
+		tile = (int64_t) 256 * 1024 * 1024 * 8 / ctx->n_ch;
 		if (tile > 65536) tile = 65536;
 		if (tile < 2048) tile = 2048;
 	}
@@ -323,12 +325,16 @@ static int enqueue_tile(gais_ctx *ctx, SampleView view, int64_t n_frames, int ti
 		signs = ctx->d_signs[tile_idx & 1];
 
 	if (timed) CK(cudaEventRecord(ctx->ev_tile[3 * tile_idx + 0], st));
-	int nl = fir_launch(ctx->cfg.fir_mode, ctx->cfg.layout, view, ctx->d_state, ctx->hist_sel, ctx->n_ch, n_frames, signs, st);
+	int hist_saved = 0;
+	int nl = fir_launch(ctx->cfg.fir_mode, ctx->cfg.layout, view, ctx->d_state, ctx->hist_sel, ctx->n_ch, n_frames, signs, st, &hist_saved);
 	if (nl < 0)
 		return fail(GAIS_ECUDA, "FIR launch failed: %s", cudaGetErrorString(cudaGetLastError()));
 	ctx->launches += nl;
-	save_hist_kernel<<<(ctx->n_ch + 127) / 128, 128, 0, st>>>(view, ctx->d_state, ctx->hist_sel, ctx->n_ch, n_frames);
-	ctx->launches++;
+	if (hist_saved < ctx->n_ch) {
+		save_hist_kernel<<<(ctx->n_ch - hist_saved + 127) / 128, 128, 0, st>>>(view, ctx->d_state, ctx->hist_sel, hist_saved, ctx->n_ch,
+										    n_frames);
+		ctx->launches++;
+	}
 	ctx->hist_sel ^= 1;
 	if (timed) CK(cudaEventRecord(ctx->ev_tile[3 * tile_idx + 1], st));
 
@@ -589,7 +595,7 @@ __global__ void export_state_kernel(const ChanState *__restrict__ st, int n, gai
 	}
 	if (cs) {
 		cs[c].pll = st[c].pll; cs[c].prev = st[c].prev; cs[c].lastbit = st[c].lastbit;
-		cs[c].fsm_state = st[c].fsm; cs[c].seqnr = st[c].seqnr; cs[c].n_bits = st[c].n_bits;
+		cs[c].fsm_state = hdlc_public_state(st[c].fsm); cs[c].seqnr = st[c].seqnr; cs[c].n_bits = st[c].n_bits;
 	}
 }
 
@@ -671,14 +677,6 @@ extern "C" int gais_get_signs(gais_ctx *ctx, uint32_t *h_words, int64_t cap_word
 	if (words > cap_words)
 		words = cap_words;
 	CK(cudaMemcpy(h_words, ctx->d_signs[0], (size_t) words * 4, cudaMemcpyDeviceToHost));
-	/* the device keeps sign words MSB first; the ABI promises bit j = sample 32w + j */
-	for (int64_t i = 0; i < words; i++) {
-		uint32_t v = h_words[i];
-		v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
-		v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
-		v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4);
-		h_words[i] = (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24);
-	}
 	return 0;
 }
 

@@ -59,7 +59,7 @@ fir_sign_exact_kernel(SampleView in, const ChanState *__restrict__ st, int hist_
 		      int64_t n_begin, int64_t n_end, int n_channels, uint32_t *__restrict__ signs)
 {
 	/* channels [c_begin, c_end), samples [n_begin, n_end) of the tile; n_begin % 32 == 0.
-	 * Sign-word format (device): MSB first, bit (31 - j) of word w = (out[32w + j] > 0). */
+	 * Sign-word format (device): LSB first, bit j of word w = (out[32w + j] > 0). */
 	__shared__ int16_t tile[K1_CH][K1_ROW];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int c = c_begin + blockIdx.x * K1_CH + warp;
@@ -92,22 +92,28 @@ fir_sign_exact_kernel(SampleView in, const ChanState *__restrict__ st, int hist_
 #pragma unroll
 	for (int j = 0; j < 32; j++) {
 		float s = exact_fir(&xs[j]);
-		word |= (s > 0.0f ? 1u : 0u) << (31 - j);
+		word |= (s > 0.0f ? 1u : 0u) << j;
 	}
 	signs[(n0 / 32 + lane) * n_channels + c] = word;
 }
 
-/* next run's history = last 36 samples seen (src/filter.c:129-134 keeps exactly these) */
-__global__ void save_hist_kernel(SampleView in, ChanState *st, int hist_sel, int n_channels, int64_t n_frames)
+/* next tile's history = last 36 samples seen (src/filter.c:129-134 keeps exactly these); channels
+ * [c_begin, n_channels) -- the fast FIR kernel saves its own */
+__global__ void save_hist_kernel(SampleView in, ChanState *st, int hist_sel, int c_begin, int n_channels, int64_t n_frames)
 {
-	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	int c = c_begin + blockIdx.x * blockDim.x + threadIdx.x;
 	if (c >= n_channels)
 		return;
 	const int16_t *row = in.base + (int64_t) c * in.ch_stride;
+	int16_t v[GAIS_NTAPS];
+#pragma unroll
 	for (int i = 0; i < GAIS_NTAPS; i++) {
 		int64_t n = n_frames - GAIS_NTAPS + i;
-		st[c].hist[hist_sel ^ 1][i] = (n < 0) ? st[c].hist[hist_sel][GAIS_NTAPS + n] : row[n * in.t_stride];
+		v[i] = (n < 0) ? st[c].hist[hist_sel][GAIS_NTAPS + n] : row[n * in.t_stride];
 	}
+#pragma unroll
+	for (int i = 0; i < GAIS_NTAPS; i++)
+		st[c].hist[hist_sel ^ 1][i] = v[i];
 }
 
 /* ------------------------------------------------------------------------------------------

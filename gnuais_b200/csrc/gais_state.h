@@ -28,7 +28,7 @@ struct ChanState {
 	uint16_t nalt, pos;
 	uint32_t n_bits;                     /* NRZI bits produced since create/reset */
 	uint32_t dacc;                       /* NRZI difference bits sliced but not yet given to the FSM */
-	uint32_t cur;                        /* partially filled word of the stored frame */
+	uint32_t cur, cur2;                  /* the last 64 stored frame bits (newest at bit 31 of cur) */
 	uint8_t nd, pad_[3];                 /* number of valid bits in dacc (< 24) */
 	uint32_t store[GAIS_STORE_WORDS];    /* stored frame bits, LSB-first */
 	int32_t ok, crcfail, sizefail;

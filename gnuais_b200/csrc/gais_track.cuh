@@ -22,15 +22,20 @@
  * "difference" accumulator (the bit that belongs to the next slice to come); a slice simply
  * moves on to the next bit, which starts at 0.  NRZI bits = ~difference bits.
  *
- * HDLC.  Difference bits are handed to the bit FSM in chunks of 24..31.  While hunting for a
- * preamble (the common state on noise) a chunk is cleared with a few bit tricks -- the FSM can
- * leave ST_SKURR only after more than 14 alternations ending in a 0 (src/protodec.c:1029-1037),
- * which a run-length test on the chunk rules out exactly; otherwise the chunk goes through the
- * per-bit FSM.  A closed frame is NOT checked here: the stored bits go to the channel's slot
- * list as a 64-byte candidate and crc_kernel / finalize_kernel (massively parallel, no
- * divergence) do CRC, counters, seqnr and the in-place compaction into gais_msg records.  The
- * reference's FSM never looks at the CRC verdict (it resets either way, src/protodec.c:1113),
- * so deferring it changes nothing observable.
+ * HDLC, branch-free.  With one lane per channel the 32 lanes of a warp sit in different FSM
+ * states, so a switch() would execute every state's code for every bit.  Instead the FSM is a
+ * transition table in shared memory: 80 states (the reachable combinations of state / nstartsign
+ * / antallpreamble / antallenner / bitstuff / last of src/protodec.h:44-71, antallpreamble
+ * saturated at 15 because only "> 14" is ever tested) x input bit -> next state + action flags
+ * (store the bit, enter DATA, frame closed).  All lanes do the same few instructions per bit.
+ * A chunk on which every lane of the warp is hunting (idle channels) is skipped with a
+ * run-length test instead.
+ *
+ * A closed frame is NOT checked here: the stored bits go to the channel's slot list as a
+ * 64-byte candidate and crc_kernel / finalize_kernel (massively parallel, no divergence) do
+ * CRC, counters, seqnr and the in-place compaction into gais_msg records.  The reference's FSM
+ * never looks at the CRC verdict (it resets either way, src/protodec.c:1113), so deferring it
+ * changes nothing observable.
  */
 #ifndef GAIS_TRACK_CUH
 #define GAIS_TRACK_CUH
@@ -42,14 +47,93 @@ namespace gais {
 #define GAIS_INC64 (GAIS_PLL_INC << 16)      /* 0x33330000: one sample of phase, in Z units */
 #define GAIS_NUDGE64 (GAIS_PLL_NUDGE << 16)
 
+/* ---- HDLC state numbering (ChanState.fsm holds these ids) --------------------------------
+ *   0..63   ST_SKURR      id = leak*32 + nalt*2 + last   (nalt = antallpreamble, saturated at 15;
+ *                         leak = the nstartsign==1 a failed ST_STARTSIGN leaves behind, :1092)
+ *   64,65   ST_PREAMBLE   nstartsign == 0, still alternating; id = 64 + last
+ *   66..70  ST_PREAMBLE   nstartsign == 1..5; id = 65 + nstartsign
+ *   71,72   ST_STARTSIGN  nstartsign == 6, 7
+ *   73      ST_DATA       last == 0
+ *   74..77  ST_DATA       last == 1, antallenner == 0..3
+ *   78      ST_DATA       bitstuff pending
+ *   79      ST_STOPSIGN
+ */
+constexpr int H_NSTATES = 80;
+constexpr uint32_t H_STORE = 0x80u, H_ENTER = 0x100u, H_EMIT = 0x200u;
+
+__host__ __device__ inline uint32_t hdlc_hunt_id(uint32_t leak, uint32_t nalt, uint32_t last)
+{
+	return leak * 32u + (nalt > 15u ? 15u : nalt) * 2u + last;
+}
+
+/* transition of state `id` on bit b: next id | action flags.  Written straight from
+ * src/protodec.c:988-1122 (the trailing "d->last = in[i]" is folded into the next id). */
+__host__ __device__ inline uint32_t hdlc_transition(uint32_t id, uint32_t b)
+{
+	if (id < 64u) {                                         /* :1028-1041 */
+		const uint32_t leak = id >> 5, nalt = (id >> 1) & 15u, last = id & 1u;
+		const uint32_t n2 = (b != last) ? (nalt < 15u ? nalt + 1u : 15u) : 0u;
+		if (n2 > 14u && b == 0u)
+			return leak ? 66u : 64u;                        /* ST_PREAMBLE, nstartsign = leak, last = 0 */
+		return hdlc_hunt_id(leak, n2, b);
+	}
+	if (id < 66u) {                                         /* :1043-1070, nstartsign == 0 */
+		const uint32_t last = id - 64u;
+		if (b != last)
+			return 64u + b;
+		return b ? 68u : 66u;                               /* nstartsign = 3 | 1 */
+	}
+	if (id < 71u) {                                         /* nstartsign = 1..5 */
+		const uint32_t k = id - 65u;
+		if (b)
+			return k == 5u ? 71u : id + 1u;
+		return hdlc_hunt_id(0, 0, 0);                       /* protodec_reset(); last = 0 */
+	}
+	if (id == 71u)                                          /* :1072-1093, nstartsign == 6 */
+		return b ? 72u : hdlc_hunt_id(1, 0, 0);             /* reset, then nstartsign++ -> 1 */
+	if (id == 72u)                                          /* nstartsign >= 7 */
+		return b ? hdlc_hunt_id(1, 0, 1) : (73u | H_ENTER);
+	if (id == 73u)                                          /* :993-1026 */
+		return (b ? 74u : 73u) | H_STORE;
+	if (id < 78u) {
+		const uint32_t n = id - 74u;
+		if (!b)
+			return 73u | H_STORE;
+		return (n == 3u ? 78u : id + 1u) | H_STORE;
+	}
+	if (id == 78u)
+		return b ? 79u : 73u;                               /* sixth one -> ST_STOPSIGN | stuffed 0 dropped */
+	return hdlc_hunt_id(0, 0, b) | H_EMIT;                  /* :1095-1115 */
+}
+
+/* ST_* value of src/protodec.h:30-34 for an id (gais_chan_state.fsm_state) */
+__host__ __device__ inline int hdlc_public_state(uint32_t id)
+{
+	return id < 64u ? GAIS_ST_HUNT : id < 71u ? GAIS_ST_PREAMBLE : id < 73u ? GAIS_ST_STARTFLAG : id < 79u ? GAIS_ST_DATA : GAIS_ST_STOPFLAG;
+}
+
 struct HdlcRegs {
-	uint32_t fsm, stuffed, last, nflag, nones, nalt, pos, cur;
+	uint32_t id;        /* state id */
+	uint32_t pos;       /* bufferpos */
+	uint32_t shi, slo;  /* the last 64 stored bits, newest at bit 31 of shi */
 };
 
-__device__ __forceinline__ void hdlc_reset(HdlcRegs &f)       /* src/protodec.c:87-100 */
+/* nibble table entry: what four input bits do to state `id` (bit 0 of v first):
+ *   bits 0..6 next id | 7..9 k = bits stored | 10..13 the stored bits (first at bit 10)
+ *   | 14 ENTER (bufferpos = 0 before storing) | 15 EMIT (frame closed) | 16..17 position of the closing bit */
+constexpr uint32_t N_ENTER = 1u << 14, N_EMIT = 1u << 15;
+
+__host__ __device__ inline uint32_t hdlc_nibble_entry(uint32_t id, uint32_t v)
 {
-	f.fsm = GAIS_ST_HUNT;
-	f.nflag = 0; f.nalt = 0; f.nones = 0; f.last = 0; f.stuffed = 0; f.pos = 0; f.cur = 0;
+	uint32_t k = 0, bits = 0, flags = 0, p = 0;
+	for (uint32_t i = 0; i < 4; i++) {
+		const uint32_t b = (v >> i) & 1u, e = hdlc_transition(id, b);
+		id = e & 0x7fu;
+		if (e & H_STORE) { bits |= b << k; k++; }
+		if (e & H_ENTER) { flags |= N_ENTER; k = 0; bits = 0; }
+		if (e & H_EMIT) { flags |= N_EMIT; p = i; }
+	}
+	return id | (k << 7) | (bits << 10) | flags | (p << 16);
 }
 
 /* candidate layout (64 B, same slot a gais_msg will occupy): words 0..13 stored bits (LSB first),
@@ -62,93 +146,103 @@ __device__ __noinline__ void hdlc_emit(const HdlcRegs &f, uint32_t b, uint32_t b
 		return;
 	}
 	uint32_t *w = reinterpret_cast<uint32_t *>(&out.slots[(int64_t) c * out.slot_cap + ncand]);
-	const uint32_t nw = f.pos >> 5;
+	const uint32_t nw = f.pos >> 5, part = (f.pos & 31u) ? f.shi >> (32u - (f.pos & 31u)) : 0u;
 #pragma unroll
 	for (uint32_t i = 0; i < 14; i++)
-		w[i] = (i < nw) ? s->store[i] : (i == nw ? f.cur : 0u);
+		w[i] = (i < nw) ? s->store[i] : (i == nw ? part : 0u);
 	w[14] = f.pos | (b << 16);
 	w[15] = bit_index;
 	ncand++;
 }
 
-/* one NRZI bit through the FSM -- src/protodec.c:988-1122, frame check deferred */
-__device__ __forceinline__ void hdlc_bit(HdlcRegs &f, uint32_t b, uint32_t bit_index, ChanState *s, int c, uint32_t &ncand,
-					 const TrackOut &out)
+/* bits [i0, i1) of W one at a time (tile tails, and nibbles in which a frame outgrows the buffer) */
+__device__ __noinline__ void hdlc_bits_serial(HdlcRegs &f, const uint16_t *__restrict__ tab, uint32_t W, uint32_t i0, uint32_t i1,
+					      uint32_t hb, ChanState *s, int c, uint32_t &ncand, const TrackOut &out)
 {
-	switch (f.fsm) {
-	case GAIS_ST_DATA:
-		if (f.stuffed) {
-			if (b) f.fsm = GAIS_ST_STOPFLAG;
-			f.stuffed = 0;
-		} else {
-			if (b == f.last && b == 1u) {
-				if (++f.nones == 4u) { f.stuffed = 1; f.nones = 0; }
-			} else {
-				f.nones = 0;
-			}
-			f.cur |= b << (f.pos & 31u);
+	for (uint32_t i = i0; i < i1; i++) {
+		const uint32_t b = (W >> i) & 1u;
+		const uint32_t e = tab[f.id * 2u + b];
+		f.id = e & 0x7fu;
+		if (e & H_STORE) {                                            /* src/protodec.c:1016-1024 */
+			f.slo = (f.slo >> 1) | (f.shi << 31);
+			f.shi = (f.shi >> 1) | (b << 31);
 			f.pos++;
-			if ((f.pos & 31u) == 0u) {
-				s->store[(f.pos >> 5) - 1u] = f.cur;
-				f.cur = 0;
+			if ((f.pos & 31u) == 0u)
+				s->store[(f.pos >> 5) - 1u] = f.shi;
+			else if (f.pos >= 449u) {
+				f.id = hdlc_hunt_id(0, 0, b);                         /* frame too long: protodec_reset() */
+				f.pos = 0;
 			}
-			if (f.pos >= 449u)
-				hdlc_reset(f);
 		}
-		break;
-	case GAIS_ST_HUNT:
-		f.nalt = (b != f.last) ? f.nalt + 1u : 0u;
-		if (f.nalt > 14u && b == 0u) { f.fsm = GAIS_ST_PREAMBLE; f.nalt = 0; }
-		break;
-	case GAIS_ST_PREAMBLE:
-		if (b != f.last && f.nflag == 0u) {
-			/* antallpreamble++ : never read before it is zeroed again */
-		} else if (b == 1u) {
-			if (f.nflag == 0u) f.nflag = 3;
-			else if (f.nflag == 5u) { f.nflag = 6; f.nalt = 0; f.fsm = GAIS_ST_STARTFLAG; }
-			else f.nflag++;
-		} else {
-			if (f.nflag == 0u) f.nflag = 1;
-			else hdlc_reset(f);
+		if (e & (H_ENTER | H_EMIT)) {
+			if (e & H_EMIT)
+				hdlc_emit(f, b, hb + i, s, c, ncand, out);
+			f.pos = 0;
 		}
-		break;
-	case GAIS_ST_STARTFLAG:
-		if (f.nflag >= 7u) {
-			if (b == 0u) { f.fsm = GAIS_ST_DATA; f.nflag = 0; f.nones = 0; f.pos = 0; f.cur = 0; }
-			else hdlc_reset(f);
-		} else if (b == 0u) {
-			hdlc_reset(f);
-		}
-		f.nflag++;                                   /* src/protodec.c:1092: even after a reset */
-		break;
-	default: /* GAIS_ST_STOPFLAG: src/protodec.c:1095-1115 */
-		hdlc_emit(f, b, bit_index, s, c, ncand, out);
-		hdlc_reset(f);
-		break;
 	}
-	f.last = b;                                          /* src/protodec.c:1119 */
 }
 
-/* n (1..31) NRZI bits, bit 0 of W the oldest; hb = index of that bit in the channel's stream */
-__device__ __forceinline__ void hdlc_chunk(HdlcRegs &f, uint32_t W, uint32_t n, uint32_t hb, ChanState *s, int c,
-					   uint32_t &ncand, const TrackOut &out)
+/* n (1..31) NRZI bits, bit 0 of W the oldest; hb = index of that bit in the channel's stream.
+ * Whole nibbles go through the nibble table; `tail` says whether the 1..3 left-over bits are
+ * consumed too (end of a tile) or left to the caller. Returns the number of bits consumed. */
+__device__ __forceinline__ uint32_t hdlc_chunk(HdlcRegs &f, const uint16_t *__restrict__ tab, const uint32_t *__restrict__ ntab,
+					       uint32_t W, uint32_t n, uint32_t hb, bool tail, ChanState *s, int c, uint32_t &ncand,
+					       const TrackOut &out)
 {
-	if (f.fsm == GAIS_ST_HUNT) {
-		const uint32_t vm = (1u << n) - 1u;
-		const uint32_t A = (W ^ ((W << 1) | f.last)) & vm;      /* bit i: b_i != b_(i-1) */
-		const uint32_t L = (uint32_t) __ffs((int) ~A) - 1u;          /* leading alternations (<= n) */
+	const uint32_t nn = n >> 2;              /* whole nibbles */
+	const uint32_t used = tail ? n : nn * 4u;
+	if (used == 0u)
+		return 0u;
+	/* warp-uniform shortcut for idle channels: while hunting, the FSM can only move on after more
+	 * than 14 alternations ending in a 0 (src/protodec.c:1029-1037); a run-length test rules that
+	 * out exactly */
+	bool fast = false;
+	uint32_t fast_id = 0;
+	if (f.id < 64u) {
+		const uint32_t leak = f.id >> 5, nalt = (f.id >> 1) & 15u, last = f.id & 1u;
+		const uint32_t vm = (used >= 32u) ? 0xffffffffu : (1u << used) - 1u;
+		const uint32_t A = (W ^ ((W << 1) | last)) & vm;          /* bit i: b_i != b_(i-1) */
+		const uint32_t L = (uint32_t) __ffs((int) ~A) - 1u;      /* leading alternations (<= used) */
 		uint32_t r = A & (A >> 1);
 		r &= r >> 2;
 		r &= r >> 4;
-		r &= r >> 7;                                                 /* a run of >= 15 alternations inside */
-		if (f.nalt + L <= 14u && r == 0u) {
-			f.nalt = (L == n) ? f.nalt + n : (uint32_t) __clz((int) ~(A << (32u - n)));
-			f.last = (W >> (n - 1u)) & 1u;
-			return;
+		r &= r >> 7;                                             /* a run of >= 15 alternations inside */
+		if (nalt + L <= 14u && r == 0u) {
+			fast = true;
+			const uint32_t n2 = (L == used) ? nalt + used : (uint32_t) __clz((int) ~(A << (32u - used)));
+			fast_id = hdlc_hunt_id(leak, n2, (W >> (used - 1u)) & 1u);
 		}
 	}
-	for (uint32_t i = 0; i < n; i++)
-		hdlc_bit(f, (W >> i) & 1u, hb + i, s, c, ncand, out);
+	if (__all_sync(__activemask(), fast)) {
+		f.id = fast_id;
+		return used;
+	}
+	for (uint32_t q = 0; q < nn; q++) {
+		const uint32_t v = (W >> (4u * q)) & 15u;
+		const uint32_t e = ntab[f.id * 16u + v];
+		const uint32_t k = (e >> 7) & 7u;
+		if (f.pos + k >= 449u && !(e & N_ENTER)) {
+			hdlc_bits_serial(f, tab, W, 4u * q, 4u * q + 4u, hb, s, c, ncand, out);   /* rare: frame outgrows the buffer */
+			continue;
+		}
+		if (e & N_ENTER)
+			f.pos = 0;
+		f.id = e & 0x7fu;
+		const uint32_t bits = (e >> 10) & 15u, pos2 = f.pos + k;
+		f.slo = __funnelshift_r(f.slo, f.shi, k);                 /* append k bits at the top of shi:slo */
+		f.shi = __funnelshift_r(f.shi, bits, k);
+		if ((f.pos ^ pos2) & 32u)                                 /* a 32-bit word of the frame is complete */
+			s->store[(pos2 >> 5) - 1u] = __funnelshift_rc(f.slo, f.shi, 32u - (pos2 & 31u));
+		f.pos = pos2;
+		if (e & N_EMIT) {
+			const uint32_t p = (e >> 16) & 3u;
+			hdlc_emit(f, (v >> p) & 1u, hb + 4u * q + p, s, c, ncand, out);
+			f.pos = 0;
+		}
+	}
+	if (tail && used > nn * 4u)
+		hdlc_bits_serial(f, tab, W, nn * 4u, used, hb, s, c, ncand, out);
+	return used;
 }
 
 /* OR n bits of W into the run-relative bit record (GAIS_KEEP_BITS); off may be negative for
@@ -170,43 +264,64 @@ __device__ __forceinline__ void bits_or(const TrackOut &out, int c, int64_t off,
 		row[(off >> 5) + 1] |= W >> (32u - sh);
 }
 
-__global__ void __launch_bounds__(128)
+constexpr int TRK_THREADS = 128;
+constexpr int TRK_PREFETCH = 4;          /* sign words loaded ahead of use (L2 latency) */
+
+__global__ void __launch_bounds__(TRK_THREADS)
 track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, int64_t n_frames, TrackOut out)
 {
+	__shared__ uint32_t ntab[H_NSTATES * 16];
+	__shared__ uint16_t tab[H_NSTATES * 2];
+	for (int i = threadIdx.x; i < H_NSTATES * 16; i += TRK_THREADS)
+		ntab[i] = hdlc_nibble_entry((uint32_t) i >> 4, (uint32_t) i & 15u);
+	for (int i = threadIdx.x; i < H_NSTATES * 2; i += TRK_THREADS)
+		tab[i] = (uint16_t) hdlc_transition((uint32_t) i >> 1, (uint32_t) i & 1u);
+	__syncthreads();
+
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
 	if (c >= n_channels)
 		return;
 	ChanState *s = &st[c];
 
 	uint32_t zlo = s->pll << 16, zhi = s->n_bits;
-	uint32_t prevword = s->prev;                 /* bit 0 = sign of the last sample seen */
-	uint32_t dlo = s->dacc, nd = s->nd;          /* difference bits not yet given to the FSM */
-	uint32_t hb = zhi - nd;                      /* stream index of dlo bit 0 */
+	uint32_t prevword = (uint32_t) s->prev << 31;   /* bit 31 = sign of the last sample seen */
+	uint32_t dlo = s->dacc, nd = s->nd;             /* difference bits not yet given to the FSM */
+	uint32_t hb = zhi - nd;                         /* stream index of dlo bit 0 */
 	HdlcRegs f;
-	f.fsm = s->fsm; f.stuffed = s->stuffed; f.last = s->last; f.nflag = s->nflag; f.nones = s->nones;
-	f.nalt = s->nalt; f.pos = s->pos; f.cur = s->cur;
+	f.id = s->fsm; f.pos = s->pos; f.shi = s->cur; f.slo = s->cur2;
 	uint32_t ncand = out.run_count[c];
 	const uint32_t zhi_start = zhi;
 	const int64_t run_start = (int64_t) zhi - (int64_t) out.run_bits[c];   /* stream index of the run's first bit */
 
 	const int64_t n_words = (n_frames + 31) >> 5;
+	const uint32_t *sp = signs + c;
+	uint32_t q[TRK_PREFETCH];
+#pragma unroll
+	for (int k = 0; k < TRK_PREFETCH; k++)
+		q[k] = (k < n_words) ? sp[(int64_t) k * n_channels] : 0u;
+
 	for (int64_t w = 0; w < n_words; w++) {
-		const uint32_t sw = signs[w * n_channels + c];
+		const uint32_t sw = q[0];
+#pragma unroll
+		for (int k = 0; k + 1 < TRK_PREFETCH; k++)
+			q[k] = q[k + 1];
+		q[TRK_PREFETCH - 1] = (w + TRK_PREFETCH < n_words) ? sp[(w + TRK_PREFETCH) * n_channels] : 0u;
 		const int64_t left = n_frames - w * 32;
 		const uint32_t nb = left < 32 ? (uint32_t) left : 32u;
-		/* MSB-first words: bit 31 is the first sample.  x marks samples whose sign differs from
-		 * the sample before */
-		uint32_t x = sw ^ __funnelshift_r(sw, prevword, 1);
+		/* LSB-first words: bit 0 is the first sample.  x marks samples whose sign differs from the
+		 * sample before */
+		uint32_t x = sw ^ __funnelshift_l(prevword, sw, 1);
 		if (nb < 32u) {
-			x &= 0xffffffffu << (32u - nb);
-			prevword = sw >> (32u - nb);
+			x &= (1u << nb) - 1u;
+			prevword = sw << (32u - nb);
 		} else {
 			prevword = sw;
 		}
 		uint32_t jp = 0;
 		while (x) {
-			const uint32_t j = (uint32_t) __clz((int) x);
-			x &= ~(0x80000000u >> j);
+			const uint32_t iso = x & (0u - x);
+			const uint32_t j = 31u - (uint32_t) __clz((int) iso);
+			x ^= iso;
 			/* samples jp .. j-1: no sign change (src/receiver.c:121-134 only) */
 			unsigned long long Z = ((unsigned long long) zhi << 32) | zlo;
 			Z += (unsigned long long) (j - jp) * GAIS_INC64;
@@ -224,34 +339,33 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 		}
 		nd = zhi - hb;
 		if (nd >= 24u) {
-			/* at most 7 slices per 32 samples, so bit 31 is never reached before this flush */
+			/* at most 7 slices per 32 samples and at most 3 bits left over from the last hand-over,
+			 * so bit 31 of dlo is never reached before this point */
 			const uint32_t W = ~dlo;
 			if (out.bits)
 				bits_or(out, c, (int64_t) hb - run_start, W, nd);
-			hdlc_chunk(f, W, nd, hb, s, c, ncand, out);
-			dlo >>= nd;
-			hb += nd;
-			nd = 0;
+			const uint32_t used = hdlc_chunk(f, tab, ntab, W, nd, hb, false, s, c, ncand, out);
+			dlo >>= used;
+			hb += used;
+			nd -= used;
 		}
 	}
 	if (nd) {
-		/* end of the tile: hand the sliced bits over now, so that FSM state, candidates and
+		/* end of the tile: hand ALL sliced bits over now, so that FSM state, candidates and
 		 * counters at a run boundary are exactly the reference's after the same samples */
 		const uint32_t W = ~dlo;
 		if (out.bits)
 			bits_or(out, c, (int64_t) hb - run_start, W, nd);
-		hdlc_chunk(f, W, nd, hb, s, c, ncand, out);
+		hdlc_chunk(f, tab, ntab, W, nd, hb, true, s, c, ncand, out);
 		dlo >>= nd;
 		hb += nd;
 		nd = 0;
 	}
 
-	s->pll = zlo >> 16; s->n_bits = zhi; s->prev = (uint8_t) (prevword & 1u);
+	s->pll = zlo >> 16; s->n_bits = zhi; s->prev = (uint8_t) (prevword >> 31);
 	s->dacc = dlo; s->nd = (uint8_t) nd;
-	s->lastbit = (uint8_t) ((prevword ^ (dlo >> nd)) & 1u);   /* sign at the last slice */
-	s->fsm = (uint8_t) f.fsm; s->stuffed = (uint8_t) f.stuffed; s->last = (uint8_t) f.last;
-	s->nflag = (uint8_t) f.nflag; s->nones = (uint8_t) f.nones;
-	s->nalt = (uint16_t) (f.nalt > 0xffffu ? 0xffffu : f.nalt); s->pos = (uint16_t) f.pos; s->cur = f.cur;
+	s->lastbit = (uint8_t) (((prevword >> 31) ^ (dlo >> nd)) & 1u);   /* sign at the last slice */
+	s->fsm = (uint8_t) f.id; s->pos = (uint16_t) f.pos; s->cur = f.shi; s->cur2 = f.slo;
 	out.run_count[c] = ncand;
 	out.run_bits[c] += zhi - zhi_start;
 }
@@ -342,7 +456,7 @@ finalize_kernel(gais_msg *__restrict__ slots, uint32_t *__restrict__ run_count, 
 static inline int track_launch(const uint32_t *signs, ChanState *st, int n_ch, int64_t n_frames, const TrackOut &out,
 			       cudaStream_t stream)
 {
-	track_kernel<<<(n_ch + 127) / 128, 128, 0, stream>>>(signs, st, n_ch, n_frames, out);
+	track_kernel<<<(n_ch + TRK_THREADS - 1) / TRK_THREADS, TRK_THREADS, 0, stream>>>(signs, st, n_ch, n_frames, out);
 	return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

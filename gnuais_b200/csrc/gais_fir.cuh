@@ -75,6 +75,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
 		"@!p bra W_%=;\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+/* producer side: poll politely, the consumers need the issue slots */
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity)
+{
+	uint32_t done = 0;
+	for (;;) {
+		asm volatile("{\n\t.reg .pred p;\n\t"
+			     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+			     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+		if (done)
+			break;
+		__nanosleep(256);
+	}
+}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -105,20 +118,36 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c)
 	return d;
 }
 
-/* ---- tier 3 for one doubtful sample; w36 -> x[n-36] inside a shared-memory row ----------- */
-__device__ __noinline__ bool fir_sign_exact(const int16_t *w36)
+/* ---- tiers 2 and 3 for one doubtful sample; w36 -> x[n-36] inside a shared-memory row ------ */
+__device__ __noinline__ bool fir_sign_resolve(const int16_t *w36)
 {
-	/* the reference's own arithmetic: float32, multiply then add, tap order (src/filter.h:40-49).
-	 * All 32 loads are issued before the dependent chain starts. */
+	/* tier 2: the 12 taps 12..23 and S12 = sum t_i |x_i|, which makes the bound data dependent:
+	 * |a12 - R| <= 0.00355 + 2.64e-6 * S12 (header comment) */
 	float xs[GAIS_NTAPS];
 #pragma unroll
-	for (int i = 2; i < GAIS_NTAPS - 2; i++)
+	for (int i = 12; i <= 23; i++)
+		xs[i] = (float) w36[i];
+	float a = 0.0f, sabs = 0.0f;
+#pragma unroll
+	for (int i = 12; i <= 23; i++) {
+		a = fmaf(xs[i], c_taps[i], a);
+		sabs = fmaf(fabsf(xs[i]), c_taps[i], sabs);
+	}
+	if (fabsf(a) > fmaf(F_E2_SLOPE, sabs, F_E2_BASE))
+		return a > 0.0f;
+	/* tier 3: the reference's own arithmetic -- float32, multiply then add, tap order
+	 * (src/filter.h:40-49).  An all-zero window gives exactly +0: not > 0. */
+#pragma unroll
+	for (int i = 2; i < 12; i++)
+		xs[i] = (float) w36[i];
+#pragma unroll
+	for (int i = 24; i < GAIS_NTAPS - 2; i++)
 		xs[i] = (float) w36[i];
 	float s = 0.0f;
 #pragma unroll
 	for (int i = 2; i < GAIS_NTAPS - 2; i++)
 		s = __fadd_rn(s, __fmul_rn(xs[i], c_taps[i]));
-	return s > 0.0f;     /* an all-zero window gives exactly +0: not > 0 */
+	return s > 0.0f;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
@@ -207,7 +236,7 @@ fir_sign_fast_kernel(const __grid_constant__ CUtensorMap tmap, const int16_t *__
 		for (int s = s_begin; s < s_end; s++) {
 			const int it = s - s_begin, buf = it % F_NSTAGE;
 			if (it >= F_NSTAGE)
-				mbar_wait(&empty_bar[buf], (uint32_t) ((it / F_NSTAGE - 1) & 1));
+				mbar_wait_sleep(&empty_bar[buf], (uint32_t) ((it / F_NSTAGE - 1) & 1));
 			uint8_t *dst = tile + buf * F_STAGE_BYTES;
 			const int64_t n0 = (int64_t) s * F_T;
 			if (s == 0) {
@@ -295,52 +324,30 @@ fir_sign_fast_kernel(const __grid_constant__ CUtensorMap tmap, const int16_t *__
 				wordB = __funnelshift_l(__float_as_uint(yb), wordB, 1);
 			}
 			if (m <= F_E1) {
-				/* some of these 16 signs are in doubt.  Tier 2, all in registers: add taps 12 and 23
-				 * to the sums we already hold.  Where even that is not decisive the output is only
-				 * MARKED; the exact chain runs after the tile column is done (no calls, no spills in
-				 * the hot loop). */
+				/* some of these 16 signs are in doubt: only MARK them here (the bits just shifted in for
+				 * them are placeholders).  They are settled after the column is done, by compact
+				 * out-of-line code, so the unrolled hot path stays small enough for the instruction cache */
 #pragma unroll
 				for (int jj = 0; jj < 8; jj++) {
-					const int j = 8 * g + jj;
 					float ya, yb;
 					unpack2(acc[jj], ya, yb);
-					if (fabsf(ya) <= F_E1 || fabsf(yb) <= F_E1) {
-						float za, zb, sa, sb;
-						unpack2(ffma2(T[0], xs[j + 11], ffma2(T[0], xs[j], acc[jj])), za, zb);
-						/* S12 = sum t_i |x_i| over the 12 taps: makes the tier-2 bound data dependent,
-						 * |a12 - R| <= 0.00355 + 2.64e-6 * S12  (see the header comment) */
-						uint64_t sacc = fmul2(T[0], abs2(xs[j]));
-#pragma unroll
-						for (int k = 1; k < 12; k++)
-							sacc = ffma2(T[k < 6 ? k : 11 - k], abs2(xs[j + k]), sacc);
-						unpack2(sacc, sa, sb);
-						if (fabsf(ya) <= F_E1) {
-							wordA = (wordA & ~(1u << (7 - jj))) | ((za < 0.0f ? 1u : 0u) << (7 - jj));
-							if (fabsf(za) <= fmaf(F_E2_SLOPE, sa, F_E2_BASE))
-								pendA |= 1u << j;
-						}
-						if (fabsf(yb) <= F_E1) {
-							wordB = (wordB & ~(1u << (7 - jj))) | ((zb < 0.0f ? 1u : 0u) << (7 - jj));
-							if (fabsf(zb) <= fmaf(F_E2_SLOPE, sb, F_E2_BASE))
-								pendB |= 1u << j;
-						}
-					}
+					if (fabsf(ya) <= F_E1)
+						pendA |= 1u << (8 * g + jj);
+					if (fabsf(yb) <= F_E1)
+						pendB |= 1u << (8 * g + jj);
 				}
 			}
 		}
 		/* device sign-word format: LSB first, bit j of word w = (filtered[32w + j] > 0) */
 		uint32_t outA = __brev(~wordA), outB = __brev(~wordB);
-		while (pendA) {      /* tier 3: x[n-36] of output j sits at row index 32*warp + j + 4 */
-			const int j = __ffs((int) pendA) - 1;
-			pendA &= pendA - 1u;
-			const bool pos = fir_sign_exact(reinterpret_cast<const int16_t *>(rowA) + 32 * warp + j + 4);
-			outA = (outA & ~(1u << j)) | ((pos ? 1u : 0u) << j);
-		}
-		while (pendB) {
-			const int j = __ffs((int) pendB) - 1;
-			pendB &= pendB - 1u;
-			const bool pos = fir_sign_exact(reinterpret_cast<const int16_t *>(rowB) + 32 * warp + j + 4);
-			outB = (outB & ~(1u << j)) | ((pos ? 1u : 0u) << j);
+		while (pendA | pendB) {      /* tiers 2 and 3: x[n-36] of output j sits at row index 32*warp + j + 4 */
+			const bool isA = pendA != 0u;
+			uint32_t &pend = isA ? pendA : pendB;
+			const int j = __ffs((int) pend) - 1;
+			pend &= pend - 1u;
+			const bool pos = fir_sign_resolve(reinterpret_cast<const int16_t *>(isA ? rowA : rowB) + 32 * warp + j + 4);
+			uint32_t &out = isA ? outA : outB;
+			out = (out & ~(1u << j)) | ((pos ? 1u : 0u) << j);
 		}
 		if (save_hist && s == n_stages - 1 && warp == F_CWARPS - 1) {
 			/* the tile ends here: its last 36 samples (row index 260..295) are the next tile's history

@@ -48,7 +48,7 @@ constexpr int F_T = 256;
 constexpr int F_HALO = 40;
 constexpr int F_ROW_BYTES = (F_T + F_HALO) * 2;     /* 592 = 80 (mod 128): 8 consecutive rows start in 8 different 16-byte bank groups */
 constexpr int F_STAGE_BYTES = F_CH * F_ROW_BYTES;   /* 37888 */
-constexpr int F_NSTAGE = 3;
+constexpr int F_NSTAGE = 2;
 constexpr int F_CWARPS = 8;                         /* consumer warps = word columns of a stage */
 constexpr int F_THREADS = (F_CWARPS + 1) * 32;      /* + one producer warp */
 constexpr int F_STAGES_PER_BLOCK = 16;              /* 4096 samples of 64 channels per CTA */
@@ -208,7 +208,7 @@ __device__ __forceinline__ void tma_g2s_2d(void *dst, const CUtensorMap *tmap, i
 		     : "memory");
 }
 
-__global__ void __launch_bounds__(F_THREADS, 2)
+__global__ void __launch_bounds__(F_THREADS, 3)
 fir_sign_fast_kernel(const __grid_constant__ CUtensorMap tmap, const int16_t *__restrict__ base, int64_t ch_stride,
 		     ChanState *__restrict__ st, int hist_sel, int n_channels, int n_stages, int stages_per_block,
 		     uint32_t *__restrict__ signs, int dbg, int save_hist)

@@ -138,26 +138,30 @@ __host__ __device__ inline uint32_t hdlc_nibble_entry(uint32_t id, uint32_t v)
 
 /* candidate layout (64 B, same slot a gais_msg will occupy): words 0..13 stored bits (LSB first),
  * word 14 = bufferpos | stop_bit << 16 (| status << 24 after crc_kernel), word 15 = closing bit index */
-__device__ __noinline__ void hdlc_emit(const HdlcRegs &f, uint32_t b, uint32_t bit_index, const ChanState *s, int c,
-				       uint32_t &ncand, const TrackOut &out)
+/* everything by value: taking the address of the per-lane FSM registers would push them to local memory */
+__device__ __noinline__ uint32_t hdlc_emit(uint32_t pos, uint32_t shi, uint32_t b, uint32_t bit_index, const ChanState *s, int c,
+					   uint32_t ncand, gais_msg *slots, int slot_cap, int32_t *overflow)
 {
-	if (ncand >= (uint32_t) out.slot_cap) {
-		*out.overflow = 1;
-		return;
+	if (ncand >= (uint32_t) slot_cap) {
+		*overflow = 1;
+		return ncand;
 	}
-	uint32_t *w = reinterpret_cast<uint32_t *>(&out.slots[(int64_t) c * out.slot_cap + ncand]);
-	const uint32_t nw = f.pos >> 5, part = (f.pos & 31u) ? f.shi >> (32u - (f.pos & 31u)) : 0u;
+	uint32_t *w = reinterpret_cast<uint32_t *>(&slots[(int64_t) c * slot_cap + ncand]);
+	const uint32_t nw = pos >> 5, part = (pos & 31u) ? shi >> (32u - (pos & 31u)) : 0u;
 #pragma unroll
 	for (uint32_t i = 0; i < 14; i++)
 		w[i] = (i < nw) ? s->store[i] : (i == nw ? part : 0u);
-	w[14] = f.pos | (b << 16);
+	w[14] = pos | (b << 16);
 	w[15] = bit_index;
-	ncand++;
+	return ncand + 1u;
 }
 
 /* bits [i0, i1) of W one at a time (tile tails, and nibbles in which a frame outgrows the buffer) */
-__device__ __noinline__ void hdlc_bits_serial(HdlcRegs &f, const uint16_t *__restrict__ tab, uint32_t W, uint32_t i0, uint32_t i1,
-					      uint32_t hb, ChanState *s, int c, uint32_t &ncand, const TrackOut &out)
+struct HdlcSerialRet { HdlcRegs f; uint32_t ncand; };
+
+__device__ __noinline__ HdlcSerialRet hdlc_bits_serial(HdlcRegs f, const uint16_t *__restrict__ tab, uint32_t W, uint32_t i0, uint32_t i1,
+						       uint32_t hb, ChanState *s, int c, uint32_t ncand, gais_msg *slots, int slot_cap,
+						       int32_t *overflow)
 {
 	for (uint32_t i = i0; i < i1; i++) {
 		const uint32_t b = (W >> i) & 1u;
@@ -176,10 +180,14 @@ __device__ __noinline__ void hdlc_bits_serial(HdlcRegs &f, const uint16_t *__res
 		}
 		if (e & (H_ENTER | H_EMIT)) {
 			if (e & H_EMIT)
-				hdlc_emit(f, b, hb + i, s, c, ncand, out);
+				ncand = hdlc_emit(f.pos, f.shi, b, hb + i, s, c, ncand, slots, slot_cap, overflow);
 			f.pos = 0;
 		}
 	}
+	HdlcSerialRet r;
+	r.f = f;
+	r.ncand = ncand;
+	return r;
 }
 
 /* n (1..31) NRZI bits, bit 0 of W the oldest; hb = index of that bit in the channel's stream.
@@ -222,7 +230,10 @@ __device__ __forceinline__ uint32_t hdlc_chunk(HdlcRegs &f, const uint16_t *__re
 		const uint32_t e = ntab[f.id * 16u + v];
 		const uint32_t k = (e >> 7) & 7u;
 		if (f.pos + k >= 449u && !(e & N_ENTER)) {
-			hdlc_bits_serial(f, tab, W, 4u * q, 4u * q + 4u, hb, s, c, ncand, out);   /* rare: frame outgrows the buffer */
+			const HdlcSerialRet r = hdlc_bits_serial(f, tab, W, 4u * q, 4u * q + 4u, hb, s, c, ncand, out.slots, out.slot_cap,
+								 out.overflow);   /* rare: frame outgrows the buffer */
+			f = r.f;
+			ncand = r.ncand;
 			continue;
 		}
 		if (e & N_ENTER)
@@ -236,12 +247,15 @@ __device__ __forceinline__ uint32_t hdlc_chunk(HdlcRegs &f, const uint16_t *__re
 		f.pos = pos2;
 		if (e & N_EMIT) {
 			const uint32_t p = (e >> 16) & 3u;
-			hdlc_emit(f, (v >> p) & 1u, hb + 4u * q + p, s, c, ncand, out);
+			ncand = hdlc_emit(f.pos, f.shi, (v >> p) & 1u, hb + 4u * q + p, s, c, ncand, out.slots, out.slot_cap, out.overflow);
 			f.pos = 0;
 		}
 	}
-	if (tail && used > nn * 4u)
-		hdlc_bits_serial(f, tab, W, nn * 4u, used, hb, s, c, ncand, out);
+	if (tail && used > nn * 4u) {
+		const HdlcSerialRet r = hdlc_bits_serial(f, tab, W, nn * 4u, used, hb, s, c, ncand, out.slots, out.slot_cap, out.overflow);
+		f = r.f;
+		ncand = r.ncand;
+	}
 	return used;
 }
 

@@ -61,6 +61,17 @@ def measured_peak():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel: str, alg_bytes: float):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r1_traffic.json), scaled to this launch's algorithmic bytes; None if no capture."""
+    p = ROOT / "profiles" / "r1_traffic.json"
+    try:
+        rec = json.loads(p.read_text())[kernel]
+        return rec["dram_bytes_per_launch"] * alg_bytes / rec["alg_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -263,13 +274,32 @@ def main():
     # 64 B per emitted record belongs to the tracking kernel
     alg_bytes = 2.0 * samples_per_launch if dom == "fir_sign" else 2.0 * samples_per_launch + 64.0 * msgs_per_launch
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+    overlap = os.environ.get("GAIS_OVERLAP", "1") != "0" and n_tiles > 1
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "avg_launch_ms": launch_ms,
+                "traffic": ncu_traffic(dom, alg_bytes), "peak_source": peak_src, "avg_launch_ms": launch_ms,
                 "alg_bytes_per_launch": alg_bytes,
+                "timing": "CUDA events on the stream each kernel is launched on, inside the timed region"
+                          + ("; FIR of tile t+1 runs CONCURRENTLY with tracking of tile t, so both launch durations "
+                             "include the other kernel's share of the SMs (see solo)" if overlap else ""),
                 "chain": {"fir_ms_per_step": acc["fir_ms"] / args.steps, "track_ms_per_step": acc["track_ms"] / args.steps,
                           "post_ms_per_step": acc["post_ms"] / args.steps,
                           "whole_chain_GBps": (2.0 * n_ch * frames + 64.0 * acc["msgs"] / args.steps)
                           / (acc["total_ms"] / args.steps * 1e-3) / 1e9}}
+    if overlap:
+        # the same kernels timed alone (overlap off), outside the timed region: 1 warm-up + 2 steps
+        rxs = BatchReceiver(n_ch, frames, device=local_rank, fir_mode=args.fir_mode, tile_frames=args.tile_frames, overlap=False)
+        solo = {"fir_ms": 0.0, "track_ms": 0.0}
+        for i in range(3):
+            rxs.run(d, stream=stream.cuda_stream)
+            rxs.sync()
+            if i:
+                tm = rxs.timing()
+                solo["fir_ms"] += tm["fir_ms"]; solo["track_ms"] += tm["track_ms"]
+        rxs.close()
+        f_ms, t_ms = solo["fir_ms"] / (2 * n_tiles), solo["track_ms"] / (2 * n_tiles)
+        roofline["solo"] = {"fir_launch_ms": f_ms, "track_launch_ms": t_ms,
+                            "fir_GBps": 2.0 * samples_per_launch / (f_ms * 1e-3) / 1e9,
+                            "fir_frac": 2.0 * samples_per_launch / (f_ms * 1e-3) / 1e9 / peak}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -79,9 +79,11 @@ struct gais_ctx {
 	unsigned long long *d_totals;
 	int16_t *d_stage[2];        /* gais_run_host staging tiles */
 	int64_t stage_elems;
-	cudaStream_t s_copy, s_own;
+	cudaStream_t s_copy, s_own, s_fir, s_trk;
+	cudaEvent_t ev_fir_done[2], ev_trk_done[2], ev_join;
+	int overlap;                /* GAIS_OVERLAP=1: FIR of tile t+1 concurrent with tracking of tile t */
 	cudaEvent_t ev[EV_COUNT], ev_copy[2], ev_free[2];
-	cudaEvent_t *ev_tile;       /* 3 per tile: fir start, fir end / track start, track end */
+	cudaEvent_t *ev_tile;       /* 4 per tile: fir start, fir end, track start, track end */
 	int ev_tile_cap;
 	cudaStream_t last_stream;
 	int pending;                /* a run has been enqueued and not finished */
@@ -158,6 +160,13 @@ extern "C" void gais_destroy(gais_ctx *ctx)
 	cudaFree(ctx->d_stage[1]);
 	if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
 	if (ctx->s_own) cudaStreamDestroy(ctx->s_own);
+	if (ctx->s_fir) cudaStreamDestroy(ctx->s_fir);
+	if (ctx->s_trk) cudaStreamDestroy(ctx->s_trk);
+	for (int i = 0; i < 2; i++) {
+		if (ctx->ev_fir_done[i]) cudaEventDestroy(ctx->ev_fir_done[i]);
+		if (ctx->ev_trk_done[i]) cudaEventDestroy(ctx->ev_trk_done[i]);
+	}
+	if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
 	for (int i = 0; i < EV_COUNT; i++)
 		if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
 	for (int i = 0; i < 2; i++) {
@@ -249,6 +258,19 @@ extern "C" int gais_create(const gais_config *cfg, gais_ctx **out)
 		}
 		CKC(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
 		CKC(cudaStreamCreateWithFlags(&ctx->s_own, cudaStreamNonBlocking));
+		{
+			int lo = 0, hi = 0;
+			CKC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+			CKC(cudaStreamCreateWithPriority(&ctx->s_fir, cudaStreamNonBlocking, lo));
+			CKC(cudaStreamCreateWithPriority(&ctx->s_trk, cudaStreamNonBlocking, hi));
+			for (int i = 0; i < 2; i++) {
+				CKC(cudaEventCreateWithFlags(&ctx->ev_fir_done[i], cudaEventDisableTiming));
+				CKC(cudaEventCreateWithFlags(&ctx->ev_trk_done[i], cudaEventDisableTiming));
+			}
+			CKC(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+			/* reserved[2]: 0 = default (on unless GAIS_OVERLAP=0), 1 = off, 2 = on */
+			ctx->overlap = cfg->reserved[2] == 1 ? 0 : cfg->reserved[2] == 2 ? 1 : (int) env_i64("GAIS_OVERLAP", 1);
+		}
 		for (int i = 0; i < EV_COUNT; i++)
 			CKC(cudaEventCreate(&ctx->ev[i]));
 		for (int i = 0; i < 2; i++) {
@@ -274,7 +296,7 @@ bad:
 
 static int ensure_tile_events(gais_ctx *ctx, int n_tiles)
 {
-	int need = n_tiles * 3;
+	int need = n_tiles * 4;
 	if (need <= ctx->ev_tile_cap)
 		return 0;
 	cudaEvent_t *ne = (cudaEvent_t *) realloc(ctx->ev_tile, sizeof(cudaEvent_t) * need);
@@ -316,15 +338,22 @@ static int enqueue_post(gais_ctx *ctx, cudaStream_t st)
 /* enqueue FIR + tracking for one time tile whose samples are at `view` (n = 0 is the first
  * sample of the tile) */
 static int enqueue_tile(gais_ctx *ctx, SampleView view, int64_t n_frames, int tile_idx, int64_t word_ofs, cudaStream_t st,
-			bool timed)
+			cudaStream_t st_trk, bool timed)
 {
+	/* st carries the FIR stage, st_trk the tracking stage.  When they differ (overlap mode) the
+	 * FIR of tile t+1 runs while tile t is being tracked; the two sign buffers are handed back and
+	 * forth with events. */
+	const bool overlap = st != st_trk;
+	const bool keep = (ctx->cfg.flags & GAIS_KEEP_SIGNS) != 0;
 	uint32_t *signs;
-	if (ctx->cfg.flags & GAIS_KEEP_SIGNS)
+	if (keep)
 		signs = ctx->d_signs[0] + word_ofs * ctx->n_ch;
 	else
 		signs = ctx->d_signs[tile_idx & 1];
 
-	if (timed) CK(cudaEventRecord(ctx->ev_tile[3 * tile_idx + 0], st));
+	if (overlap && !keep && tile_idx >= 2)
+		CK(cudaStreamWaitEvent(st, ctx->ev_trk_done[tile_idx & 1], 0));   /* buffer still being read by tile t-2 */
+	if (timed) CK(cudaEventRecord(ctx->ev_tile[4 * tile_idx + 0], st));
 	int hist_saved = 0;
 	int nl = fir_launch(ctx->cfg.fir_mode, ctx->cfg.layout, view, ctx->d_state, ctx->hist_sel, ctx->n_ch, n_frames, signs, st, &hist_saved);
 	if (nl < 0)
@@ -336,14 +365,21 @@ static int enqueue_tile(gais_ctx *ctx, SampleView view, int64_t n_frames, int ti
 		ctx->launches++;
 	}
 	ctx->hist_sel ^= 1;
-	if (timed) CK(cudaEventRecord(ctx->ev_tile[3 * tile_idx + 1], st));
+	if (timed) CK(cudaEventRecord(ctx->ev_tile[4 * tile_idx + 1], st));
+	if (overlap) {
+		CK(cudaEventRecord(ctx->ev_fir_done[tile_idx & 1], st));
+		CK(cudaStreamWaitEvent(st_trk, ctx->ev_fir_done[tile_idx & 1], 0));
+	}
 
+	if (timed) CK(cudaEventRecord(ctx->ev_tile[4 * tile_idx + 2], st_trk));
 	TrackOut out = make_out(ctx);
-	nl = track_launch(signs, ctx->d_state, ctx->n_ch, n_frames, out, st);
+	nl = track_launch(signs, ctx->d_state, ctx->n_ch, n_frames, out, st_trk);
 	if (nl < 0)
 		return fail(GAIS_ECUDA, "tracking launch failed: %s", cudaGetErrorString(cudaGetLastError()));
 	ctx->launches += nl;
-	if (timed) CK(cudaEventRecord(ctx->ev_tile[3 * tile_idx + 2], st));
+	if (timed) CK(cudaEventRecord(ctx->ev_tile[4 * tile_idx + 3], st_trk));
+	if (overlap)
+		CK(cudaEventRecord(ctx->ev_trk_done[tile_idx & 1], st_trk));
 	CK(cudaGetLastError());
 	return 0;
 }
@@ -380,6 +416,14 @@ extern "C" int gais_run_device(gais_ctx *ctx, const int16_t *d_samples, int64_t 
 	if ((rc = ensure_tile_events(ctx, n_tiles)) != 0)
 		return rc;
 	CK(cudaEventRecord(ctx->ev[EV_START], st));
+	/* overlap mode: FIR on s_fir, tracking on the high-priority s_trk, both forked from / joined to st */
+	cudaStream_t sF = st, sT = st;
+	if (ctx->overlap && n_tiles > 1) {
+		sF = ctx->s_fir;
+		sT = ctx->s_trk;
+		CK(cudaStreamWaitEvent(sF, ctx->ev[EV_START], 0));
+		CK(cudaStreamWaitEvent(sT, ctx->ev[EV_START], 0));
+	}
 	for (int t = 0; t < n_tiles; t++) {
 		int64_t f0 = (int64_t) t * ctx->tile_frames;
 		int64_t nf = (n_frames - f0 < ctx->tile_frames) ? n_frames - f0 : ctx->tile_frames;
@@ -387,11 +431,15 @@ extern "C" int gais_run_device(gais_ctx *ctx, const int16_t *d_samples, int64_t 
 		v.ch_stride = planar ? stride : 1;
 		v.t_stride = planar ? 1 : stride;
 		v.base = d_samples + f0 * v.t_stride;
-		if ((rc = enqueue_tile(ctx, v, nf, t, f0 / 32, st, true)) != 0)
+		if ((rc = enqueue_tile(ctx, v, nf, t, f0 / 32, sF, sT, true)) != 0)
 			return rc;
 	}
-	if ((rc = enqueue_post(ctx, st)) != 0)
+	if ((rc = enqueue_post(ctx, sT)) != 0)
 		return rc;
+	if (sT != st) {
+		CK(cudaEventRecord(ctx->ev_join, sT));
+		CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+	}
 	CK(cudaEventRecord(ctx->ev[EV_END], st));
 	CK(cudaGetLastError());
 	ctx->last_stream = st;
@@ -449,7 +497,7 @@ extern "C" int gais_run_host(gais_ctx *ctx, const int16_t *h_samples, int64_t n_
 		}
 		CK(cudaEventRecord(ctx->ev_copy[b], ctx->s_copy));
 		CK(cudaStreamWaitEvent(st, ctx->ev_copy[b], 0));
-		if ((rc = enqueue_tile(ctx, v, nf, t, f0 / 32, st, true)) != 0)
+		if ((rc = enqueue_tile(ctx, v, nf, t, f0 / 32, st, st, true)) != 0)
 			return rc;
 		CK(cudaEventRecord(ctx->ev_free[b], st));
 	}
@@ -503,9 +551,9 @@ static int finish(gais_ctx *ctx)
 	CK(cudaEventElapsedTime(&ms, ctx->ev[EV_START], ctx->ev[EV_END]));
 	tm.total_ms = ms;
 	for (int t = 0; t < ctx->n_tiles_last; t++) {
-		CK(cudaEventElapsedTime(&ms, ctx->ev_tile[3 * t], ctx->ev_tile[3 * t + 1]));
+		CK(cudaEventElapsedTime(&ms, ctx->ev_tile[4 * t], ctx->ev_tile[4 * t + 1]));
 		tm.fir_ms += ms;
-		CK(cudaEventElapsedTime(&ms, ctx->ev_tile[3 * t + 1], ctx->ev_tile[3 * t + 2]));
+		CK(cudaEventElapsedTime(&ms, ctx->ev_tile[4 * t + 2], ctx->ev_tile[4 * t + 3]));
 		tm.track_ms += ms;
 	}
 	CK(cudaEventElapsedTime(&ms, ctx->ev[EV_POST0], ctx->ev[EV_POST1]));

@@ -179,7 +179,12 @@ __device__ __forceinline__ uint64_t cvt_pair(uint32_t ua, uint32_t ub, uint32_t 
 	/* ua/ub: biased packed int16 pairs of rows A/B; sel picks the low (0x7610) or high (0x7632) half */
 	const uint32_t fa = __byte_perm(ua, F_MAGIC_BITS, sel);
 	const uint32_t fb = __byte_perm(ub, F_MAGIC_BITS, sel);
+#ifdef GAIS_FIR_SCALAR_CVT
+	(void) sub;
+	return pack2(__fadd_rn(__uint_as_float(fa), F_MAGIC_SUB), __fadd_rn(__uint_as_float(fb), F_MAGIC_SUB));
+#else
 	return fadd2(pack2(__uint_as_float(fa), __uint_as_float(fb)), sub);
+#endif
 }
 
 /* 8 samples of rows A and B -> 8 packed (A, B) float pairs */

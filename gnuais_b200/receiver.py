@@ -37,7 +37,7 @@ class BatchReceiver:
 
     def __init__(self, n_channels: int, max_frames_per_run: int, layout: str = "planar", device: int = 0,
                  fir_mode: str = "guard", keep_bits: bool = False, keep_signs: bool = False,
-                 slot_cap: int = 0, tile_frames: int = 0):
+                 slot_cap: int = 0, tile_frames: int = 0, overlap=None):
         self._lib = L.load()
         self._ctx = C.c_void_p()
         cfg = L.Config()
@@ -50,6 +50,7 @@ class BatchReceiver:
         cfg.flags = (L.KEEP_BITS if keep_bits else 0) | (L.KEEP_SIGNS if keep_signs else 0)
         cfg.reserved[0] = slot_cap
         cfg.reserved[1] = tile_frames
+        cfg.reserved[2] = 0 if overlap is None else (2 if overlap else 1)
         L.check(self._lib.gais_create(C.byref(cfg), C.byref(self._ctx)))
         self.n_channels = n_channels
         self.layout = layout

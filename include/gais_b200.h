@@ -76,7 +76,9 @@ typedef struct gais_config {
 	int64_t max_frames_per_run; /* upper bound on n_frames of one gais_run_* call */
 	int32_t fir_mode;           /* GAIS_FIR_* */
 	uint32_t flags;             /* GAIS_KEEP_* */
-	int32_t reserved[8];        /* must be 0 */
+	int32_t reserved[8];        /* tuning knobs, 0 = library default:
+	                               [0] message slots per channel per run, [1] time-tile length in frames,
+	                               [2] FIR/tracking overlap across tiles (1 = off, 2 = on); [3..7] must be 0 */
 } gais_config;
 
 /* One CRC-ok HDLC frame, 64 bytes.  payload[j] is byte j of the frame as the reference packs

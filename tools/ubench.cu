@@ -28,7 +28,10 @@
 	X(14, "popc          ", "popc.b32 %0, %0;", "r") \
 	X(15, "max.s16x2     ", "max.s16x2 %0, %0, %1;", "r") \
 	X(16, "brev          ", "brev.b32 %0, %0;", "r") \
-	X(17, "bfe.u32       ", "bfe.u32 %0, %0, 3, 9;", "r")
+	X(17, "bfe.u32       ", "bfe.u32 %0, %0, 3, 9;", "r") \
+	X(18, "cvt.f32.s32   ", "cvt.rn.f32.s32 %0, %0;", "r") \
+	X(20, "isetp+selp    ", "{ .reg .pred q; setp.lt.s32 q, %0, %1; selp.b32 %0, %1, %2, q; }", "r") \
+	X(21, "mov           ", "mov.b32 %0, %1;", "r")
 
 template <int OP>
 __global__ void __launch_bounds__(1024) k_int(uint32_t *out, int iters, unsigned long long *cyc)

@@ -86,9 +86,14 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """timed region starts now: remember how many samples were taken before it"""
+        self.t_mark = time.time()
+
     def stop(self):
         if self.proc is None:
             return None
+        time.sleep(0.15)          # let the last in-region sample land
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
@@ -97,7 +102,12 @@ class ClockSampler:
             out = ""
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.splitlines():
+        lines = out.splitlines()
+        # keep the samples of the timed region: the last ceil(region / 100 ms) + 1 lines
+        if getattr(self, "t_mark", None) is not None:
+            keep = int((time.time() - self.t_mark) / 0.1) + 1
+            lines = lines[-keep:] if keep < len(lines) else lines
+        for line in lines:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
@@ -229,10 +239,13 @@ def main():
             acc["launches"] += tm["launches"]
             acc["msgs"] += rx.message_count()
 
+    # nvidia-smi needs a moment to start: launch it before the warm-up steps so that it is sampling
+    # (every 100 ms) by the time the timed region begins; samples are kept only from the timed region
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 0)):
         step(False)
-
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()

@@ -110,6 +110,7 @@ SYMBOLS = {
     "gais_get_signs": (C.c_int, [_P, _P, C.c_int64]),
     "gais_get_timing": (C.c_int, [_P, C.POINTER(Timing)]),
     "gais_nmea_format": (C.c_int, [C.POINTER(Msg), C.c_char_p]),
+    "gais_text_format": (C.c_int, [C.POINTER(Msg), C.c_char, C.c_char_p, C.c_int]),
     "gais_synth_host": (C.c_int, [C.POINTER(Synth), C.c_uint32, C.c_int32, C.c_int64, _P, C.c_int32, C.c_int64]),
     "gais_synth_device": (C.c_int, [C.POINTER(Synth), C.c_uint32, C.c_int32, C.c_int64, _P, C.c_int32, C.c_int64, _P]),
 }

@@ -24,6 +24,7 @@ struct shim {
 	int64_t queued, batch;
 	gais_msg *msgs;
 	int64_t msgs_cap;
+	int print_stdout;
 };
 
 static void die(const char *what)
@@ -44,6 +45,7 @@ struct receiver *init_receiver(char name, int num_ch, int ch_ofs, struct serial_
 	if (!rx || !d || !s)
 		exit(1);                              /* hmalloc() exits on OOM, src/hmalloc.c:40-55 */
 	s->batch = (e && atoll(e) > 0) ? atoll(e) : 48000;
+	s->print_stdout = !(getenv("GAIS_SHIM_STDOUT") && atoi(getenv("GAIS_SHIM_STDOUT")) == 0);
 	s->queue = (int16_t *) malloc(sizeof(int16_t) * (size_t) (s->batch + 4096));
 	if (!s->queue)
 		exit(1);
@@ -100,6 +102,7 @@ void gais_compat_flush(struct receiver *rx)
 		die("receiver_run");
 	for (int64_t i = 0; i < n; i++) {
 		char text[GAIS_NMEA_STRIDE + 1];
+		char line[1024];
 		int len = gais_nmea_format(&s->msgs[i], text), pos = 0;
 		while (pos < len) {                   /* one or two "!AIVDM...\r\n" sentences */
 			int end = pos;
@@ -111,6 +114,12 @@ void gais_compat_flush(struct receiver *rx)
 			if (d->ipc && ipc_write)
 				ipc_write(d->ipc, text + pos, end - pos - 2);
 			pos = end;
+		}
+		/* the per-message stdout line of protodec_getdata() (src/protodec.c:934-985; skip_type[] is
+		 * the host program's configuration and is not visible here: GAIS_SHIM_STDOUT=0 silences it) */
+		if (s->print_stdout && gais_text_format(&s->msgs[i], d->chanid, line, (int) sizeof(line)) > 0) {
+			fputs(line, stdout);
+			fflush(stdout);
 		}
 	}
 	if (gais_get_counters(s->ctx, &cnt) != 0 || gais_get_state(s->ctx, &st) != 0)

@@ -202,6 +202,15 @@ def nmea_format(msg) -> bytes:
     return buf.raw[:n]
 
 
+def text_format(msg, chanid: str = "A") -> bytes:
+    """The stdout line gnuais prints for one MSG_DTYPE record (src/protodec.c:931-985)."""
+    lib = L.load()
+    m = L.Msg.from_buffer_copy(np.asarray(msg).tobytes())
+    buf = C.create_string_buffer(1024)
+    n = lib.gais_text_format(C.byref(m), chanid.encode()[:1], buf, 1024)
+    return buf.raw[:max(n, 0)]
+
+
 # ---- single-channel mirror of the reference's receiver.h ------------------------------------
 
 class _Decoder:

@@ -176,6 +176,13 @@ int gais_get_timing(gais_ctx *ctx, gais_timing *out);
  * shim).  out must hold GAIS_NMEA_STRIDE bytes; returns the text length (0 if gated). */
 int gais_nmea_format(const gais_msg *msg, char *out);
 
+/* The text line gnuais prints to stdout for a message:
+ *   "ch %c type %d mmsi %09ld:<fields> (!AIVDM,...)\n"
+ * protodec_getdata() src/protodec.c:931-985 + the field decoders src/protodec.c:216-776 (stdout text
+ * only; the MySQL/cache/range sinks are not fed).  Host-side, per message.  Returns the length
+ * written (0 when the type gate drops the message), out needs >= 512 bytes. */
+int gais_text_format(const gais_msg *msg, char chanid, char *out, int cap);
+
 /* ---- synthetic workload; integer-only, host and device agree bit-for-bit -- */
 
 typedef struct gais_synth {

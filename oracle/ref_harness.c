@@ -35,6 +35,7 @@
 #include "protodec.h"
 #include "cfg.h"
 #include "hlog.h"
+extern void protodec_deinit(struct demod_state_t *d);
 #include <syslog.h>
 
 /* ---- taps (only live in the *_tap.so link; harmless otherwise) ------------------------- */
@@ -90,6 +91,61 @@ void gref_set_quiet(int quiet)
 	/* the "Level on ch A too high" notice of src/receiver.c:137-147 is wall-clock gated
 	 * diagnostics on stderr, not a parity output: raise the hlog threshold above it */
 	log_level = quiet ? LOG_ERR : LOG_INFO;
+}
+
+/* capture what the reference printf()s (the per-message line of src/protodec.c:934-985) */
+static int cap_saved = -1, cap_fd = -1;
+int gref_stdout_begin(void)
+{
+	fflush(stdout);
+	cap_fd = memfd_create("gref_stdout", 0);
+	cap_saved = dup(1);
+	if (cap_fd < 0 || cap_saved < 0)
+		return -1;
+	dup2(cap_fd, 1);
+	return 0;
+}
+int64_t gref_stdout_end(char *out, int64_t cap)
+{
+	int64_t got = 0;
+	fflush(stdout);
+	dup2(cap_saved, 1);
+	close(cap_saved);
+	off_t sz = lseek(cap_fd, 0, SEEK_END);
+	lseek(cap_fd, 0, SEEK_SET);
+	while (got < sz && got < cap) {
+		ssize_t n = read(cap_fd, out + got, (size_t) ((sz < cap ? sz : cap) - got));
+		if (n <= 0)
+			break;
+		got += n;
+	}
+	close(cap_fd);
+	cap_fd = cap_saved = -1;
+	return (int64_t) sz;
+}
+
+/*
+ * The reference's per-message text for one CRC-ok frame: fills a demod_state_t the way
+ * protodec_calculate_crc() leaves it (src/protodec.c:150-162: rbuffer[k] = payload bit k for the
+ * nbits/8 whole bytes, 0 beyond) and calls protodec_getdata() (src/protodec.c:896-986) with stdout
+ * captured.  Returns the number of bytes the reference printed.
+ */
+int64_t gref_getdata_text(const uint8_t *payload, int nbits, int seqnr, char chanid, char *out, int64_t cap)
+{
+	struct demod_state_t d;
+	int nb = nbits / 8;
+	int64_t n;
+	protodec_initialize(&d, NULL, NULL, chanid);
+	d.seqnr = (unsigned char) seqnr;
+	memset(d.rbuffer, 0, DEMOD_BUFFER_LEN);
+	for (int k = 0; k < 8 * nb && k < DEMOD_BUFFER_LEN; k++)
+		d.rbuffer[k] = (payload[k >> 3] >> (7 - (k & 7))) & 1;
+	if (gref_stdout_begin() != 0)
+		return -1;
+	protodec_getdata(nbits, &d);
+	n = gref_stdout_end(out, cap);
+	protodec_deinit(&d);
+	return n;
 }
 
 /*

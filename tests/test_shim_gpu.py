@@ -8,6 +8,7 @@ import pytest
 
 import cases
 import oracle_lib as O
+from gnuais_b200 import MSG_DTYPE, text_format
 
 ROOT = Path(__file__).resolve().parent.parent
 LIBDIR = ROOT / "gnuais_b200" / "lib"
@@ -40,10 +41,25 @@ def test_shim_matches_reference_loop(tmp_path, channels):
                        env={"GAIS_SHIM_BATCH_FRAMES": "48000", "PATH": "/usr/bin:/bin"})
     assert r.returncode == 0, r.stderr
     lines = r.stdout.strip().splitlines()
+    stats = [ln for ln in lines if ": Received correctly:" in ln]
     for c in range(channels):
-        want = O.port().run(x, num_ch=channels, ch_ofs=c)
+        want = O.port().run(x, num_ch=channels, ch_ofs=c, want_frames=True)
         got = (tmp_path / f"out.{'AB'[c]}.nmea").read_bytes()
         assert got == want.nmea
-        assert lines[c] == (f"{'AB'[c]}: Received correctly: {want.ok} packets, wrong CRC: {want.crcfail} packets, "
+        assert stats[c] == (f"{'AB'[c]}: Received correctly: {want.ok} packets, wrong CRC: {want.crcfail} packets, "
                             f"wrong size: {want.sizefail} packets")
         assert want.ok > 50
+        # the per-message stdout lines (src/protodec.c:934-985), in order, for this channel
+        text = [ln for ln in lines if ln.startswith(f"ch {'AB'[c]} type ")]
+        seq, expect = 0, []
+        for f in want.frames[want.frames["status"] == 0]:
+            m = np.zeros((), dtype=MSG_DTYPE)
+            nb = int(f["nbytes"])
+            m["payload"][:nb] = f["payload"][:nb]
+            m["nbits"] = f["nbits"]
+            gate = 1 <= (int(f["payload"][0]) >> 2) <= 24
+            m["flags"] = seq | (16 if gate else 0)
+            if gate:
+                seq = (seq + 1) % 10
+                expect.append(text_format(m, "AB"[c]).decode().rstrip("\n"))
+        assert text == expect

@@ -224,14 +224,20 @@ def main():
     acc = {"fir_ms": 0.0, "track_ms": 0.0, "post_ms": 0.0, "total_ms": 0.0, "launches": 0, "tiles": 0, "msgs": 0,
            "gather_bytes": 0}
 
+    pending = {"gather": None}
+
     def step(timed: bool):
         rx.run(d, stream=stream.cuda_stream)
         rx.sync()
         if world > 1:
+            # collect the decoded messages on rank 0.  The transfer of step k rides NCCL's stream while
+            # step k+1 computes; it is completed before the next transfer starts and before the clock stops
             recs = gdist.globalize_channels(gdist.device_records(rx), first_channel)
-            out = gdist.gather_records(recs, dst=0)
-            if timed and out is not None:
-                acc["gather_bytes"] += int(out.numel())
+            if pending["gather"] is not None:
+                out = pending["gather"].wait()
+                if timed and out is not None:
+                    acc["gather_bytes"] += int(out.numel())
+            pending["gather"] = gdist.gather_records_async(recs, dst=0)
         if timed:
             tm = rx.timing()
             for k in ("fir_ms", "track_ms", "post_ms", "total_ms"):
@@ -239,11 +245,19 @@ def main():
             acc["launches"] += tm["launches"]
             acc["msgs"] += rx.message_count()
 
+    def drain(timed: bool):
+        if pending["gather"] is not None:
+            out = pending["gather"].wait()
+            pending["gather"] = None
+            if timed and out is not None:
+                acc["gather_bytes"] += int(out.numel())
+
     # nvidia-smi needs a moment to start: launch it before the warm-up steps so that it is sampling
     # (every 100 ms) by the time the timed region begins; samples are kept only from the timed region
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 0)):
         step(False)
+    drain(False)
     if sampler:
         sampler.mark()
     if world > 1:
@@ -253,6 +267,7 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         step(True)
+    drain(True)
     e1.record(stream)
     torch.cuda.synchronize()
     if world > 1:

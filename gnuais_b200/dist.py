@@ -79,6 +79,47 @@ def gather_records(records: torch.Tensor, dst: int = 0, group=None) -> Optional[
     return None
 
 
+class PendingGather:
+    """An in-flight gather_records(): the sends/receives run on NCCL's stream while the caller goes
+    on computing; wait() completes them and returns the concatenation on dst (None elsewhere)."""
+
+    def __init__(self, reqs, out, keep):
+        self._reqs, self._out, self._keep = reqs, out, keep
+
+    def wait(self):
+        for r in self._reqs:
+            r.wait()
+        self._reqs, self._keep = [], None
+        return self._out
+
+
+def gather_records_async(records: torch.Tensor, dst: int = 0, group=None) -> PendingGather:
+    """Like gather_records(), but returns as soon as the transfers are enqueued.  `records` must not
+    be modified until wait() (pass a private copy, e.g. the result of globalize_channels())."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n_local = torch.tensor([records.shape[0]], dtype=torch.int64, device=records.device)
+    counts = torch.zeros(world, dtype=torch.int64, device=records.device)
+    dist.all_gather_into_tensor(counts, n_local, group=group)
+    counts = counts.cpu().tolist()
+    if rank == dst:
+        out = torch.empty((sum(counts), REC_BYTES), dtype=torch.uint8, device=records.device)
+        offs = [0]
+        for c in counts:
+            offs.append(offs[-1] + c)
+        ops = []
+        for r in range(world):
+            if counts[r] == 0:
+                continue
+            if r == dst:
+                out[offs[r]:offs[r + 1]].copy_(records)
+            else:
+                ops.append(dist.P2POp(dist.irecv, out[offs[r]:offs[r + 1]], r, group=group))
+        return PendingGather(dist.batch_isend_irecv(ops) if ops else [], out, records)
+    ops = [dist.P2POp(dist.isend, records.contiguous(), dst, group=group)] if counts[rank] > 0 else []
+    return PendingGather(dist.batch_isend_irecv(ops) if ops else [], None, records)
+
+
 def reduce_totals(totals, dst: int = 0, group=None, device="cpu"):
     """sum of (ok, crcfail, sizefail) over ranks"""
     t = torch.tensor(list(totals), dtype=torch.int64, device=device)

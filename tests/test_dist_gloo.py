@@ -41,6 +41,8 @@ def _worker(rank, world, port, total_channels, seed, out_path):
     recs = torch.from_numpy(local.view(np.uint8).reshape(-1, 64).copy())
     recs = gdist.globalize_channels(recs, first)
     got = gdist.gather_records(recs, dst=0)
+    got2 = gdist.gather_records_async(recs.clone(), dst=0).wait()      # the overlapped form bench.py uses
+    assert (got is None and got2 is None) or torch.equal(got, got2)
     tot = gdist.reduce_totals((len(local), rank, 1))
     if rank == 0:
         np.save(out_path, got.numpy())

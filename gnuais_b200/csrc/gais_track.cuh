@@ -280,8 +280,11 @@ __device__ __forceinline__ void bits_or(const TrackOut &out, int c, int64_t off,
 
 constexpr int TRK_THREADS = 128;
 constexpr int TRK_PREFETCH = 4;          /* sign words loaded ahead of use (L2 latency) */
+#ifndef TRK_MIN_BLOCKS
+#define TRK_MIN_BLOCKS 1
+#endif
 
-__global__ void __launch_bounds__(TRK_THREADS)
+__global__ void __launch_bounds__(TRK_THREADS, TRK_MIN_BLOCKS)
 track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, int64_t n_frames, TrackOut out)
 {
 	__shared__ uint32_t ntab[H_NSTATES * 16];

@@ -49,50 +49,71 @@ constexpr int F_HALO = 40;
 constexpr int F_ROW_BYTES = (F_T + F_HALO) * 2;     /* 592 = 80 (mod 128): 8 consecutive rows start in 8 different 16-byte bank groups */
 constexpr int F_STAGE_BYTES = F_CH * F_ROW_BYTES;   /* 37888 */
 constexpr int F_NSTAGE = 2;
-constexpr int F_CWARPS = 8;                         /* consumer warps = word columns of a stage */
-constexpr int F_THREADS = (F_CWARPS + 1) * 32;      /* + one producer warp */
+#ifndef F_OUT_WORDS
+#define F_OUT_WORDS 1                               /* sign words (32 outputs) per lane per stage */
+#endif
+#ifndef F_MIN_BLOCKS
+#define F_MIN_BLOCKS 3
+#endif
+constexpr int F_W = F_OUT_WORDS;
+constexpr int F_CWARPS = F_T / (32 * F_W);          /* warps of a CTA: each owns F_W word columns of a stage */
+constexpr int F_THREADS = F_CWARPS * 32;
 constexpr int F_STAGES_PER_BLOCK = 16;              /* 4096 samples of 64 channels per CTA */
 #define F_E1 0.5f
 #define F_E2_BASE 0.004f       /* 2 * 0.001775 (taps <= 11 / >= 24 at full scale) rounded up */
 #define F_E2_SLOPE 3.0e-6f     /* (gamma_32 + 12 u) = 2.64e-6 rounded up */
 
-/* ---- small PTX helpers --------------------------------------------------------------- */
+/* ---- small PTX helpers (all shared-memory operands are 32-bit shared-window addresses) ---- */
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
 	asm volatile(
 		"{\n\t.reg .pred p;\n\t"
 		"W_%=:\n\t"
 		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-		"@!p bra W_%=;\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+		"@!p bra W_%=;\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
-/* producer side: poll politely, the consumers need the issue slots */
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
-	uint32_t done = 0;
-	for (;;) {
-		asm volatile("{\n\t.reg .pred p;\n\t"
-			     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-			     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-		if (done)
-			break;
-		__nanosleep(256);
-	}
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-		     "l"(src), "r"(bytes), "r"(smem_u32(bar))
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+		     "r"(bytes), "r"(bar)
 		     : "memory");
+}
+/* one TMA request per stage: box = 64 rows x 148 uint32 (= 296 int16) of the planar sample matrix */
+__device__ __forceinline__ void tma_g2s_2d(uint32_t dst, const CUtensorMap *tmap, int x, int y, uint32_t bar)
+{
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+		     "l"(tmap), "r"(x), "r"(y), "r"(bar)
+		     : "memory");
+}
+/* "this warp is done reading the buffer": acq_rel, so that the warp which counts the last arrival has
+ * every other warp's reads of the buffer ordered before the refill it issues */
+__device__ __forceinline__ uint32_t smem_add_acq_rel(uint32_t addr, uint32_t v)
+{
+	uint32_t old;
+	asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+	return old;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ float lds_s16_f32(uint32_t addr)
+{
+	short v;
+	asm volatile("ld.shared.s16 %0, [%1];" : "=h"(v) : "r"(addr));
+	return (float) v;
 }
 
 __device__ __forceinline__ uint64_t pack2(float lo, float hi)
@@ -117,16 +138,22 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c)
 	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
 	return d;
 }
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b)
+{
+	uint64_t d;
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+	return d;
+}
 
-/* ---- tiers 2 and 3 for one doubtful sample; w36 -> x[n-36] inside a shared-memory row ------ */
-__device__ __noinline__ bool fir_sign_resolve(const int16_t *w36)
+/* ---- tiers 2 and 3 for one doubtful sample; w36 = shared address of x[n-36] inside a row ------ */
+__device__ __noinline__ uint32_t fir_sign_resolve(uint32_t w36)
 {
 	/* tier 2: the 12 taps 12..23 and S12 = sum t_i |x_i|, which makes the bound data dependent:
 	 * |a12 - R| <= 0.00355 + 2.64e-6 * S12 (header comment) */
 	float xs[GAIS_NTAPS];
 #pragma unroll
 	for (int i = 12; i <= 23; i++)
-		xs[i] = (float) w36[i];
+		xs[i] = lds_s16_f32(w36 + 2 * i);
 	float a = 0.0f, sabs = 0.0f;
 #pragma unroll
 	for (int i = 12; i <= 23; i++) {
@@ -134,34 +161,20 @@ __device__ __noinline__ bool fir_sign_resolve(const int16_t *w36)
 		sabs = fmaf(fabsf(xs[i]), c_taps[i], sabs);
 	}
 	if (fabsf(a) > fmaf(F_E2_SLOPE, sabs, F_E2_BASE))
-		return a > 0.0f;
+		return a > 0.0f ? 1u : 0u;
 	/* tier 3: the reference's own arithmetic -- float32, multiply then add, tap order
 	 * (src/filter.h:40-49).  An all-zero window gives exactly +0: not > 0. */
 #pragma unroll
 	for (int i = 2; i < 12; i++)
-		xs[i] = (float) w36[i];
+		xs[i] = lds_s16_f32(w36 + 2 * i);
 #pragma unroll
 	for (int i = 24; i < GAIS_NTAPS - 2; i++)
-		xs[i] = (float) w36[i];
+		xs[i] = lds_s16_f32(w36 + 2 * i);
 	float s = 0.0f;
 #pragma unroll
 	for (int i = 2; i < GAIS_NTAPS - 2; i++)
 		s = __fadd_rn(s, __fmul_rn(xs[i], c_taps[i]));
-	return s > 0.0f;
-}
-
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ uint64_t abs2(uint64_t a) { return a & 0x7fffffff7fffffffull; }
-
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b)
-{
-	uint64_t d;
-	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-	return d;
+	return s > 0.0f ? 1u : 0u;
 }
 
 /*
@@ -179,19 +192,14 @@ __device__ __forceinline__ uint64_t cvt_pair(uint32_t ua, uint32_t ub, uint32_t 
 	/* ua/ub: biased packed int16 pairs of rows A/B; sel picks the low (0x7610) or high (0x7632) half */
 	const uint32_t fa = __byte_perm(ua, F_MAGIC_BITS, sel);
 	const uint32_t fb = __byte_perm(ub, F_MAGIC_BITS, sel);
-#ifdef GAIS_FIR_SCALAR_CVT
-	(void) sub;
-	return pack2(__fadd_rn(__uint_as_float(fa), F_MAGIC_SUB), __fadd_rn(__uint_as_float(fb), F_MAGIC_SUB));
-#else
 	return fadd2(pack2(__uint_as_float(fa), __uint_as_float(fb)), sub);
-#endif
 }
 
 /* 8 samples of rows A and B -> 8 packed (A, B) float pairs */
-__device__ __forceinline__ void fir_load_chunk(uint64_t *xs, const uint8_t *rowA, const uint8_t *rowB, int byte_ofs, uint64_t sub)
+__device__ __forceinline__ void fir_load_chunk(uint64_t *xs, uint32_t rowA, uint32_t rowB, int byte_ofs, uint64_t sub)
 {
-	uint4 a = *reinterpret_cast<const uint4 *>(rowA + byte_ofs);
-	uint4 b = *reinterpret_cast<const uint4 *>(rowB + byte_ofs);
+	uint4 a = lds128(rowA + byte_ofs);
+	uint4 b = lds128(rowB + byte_ofs);
 	a.x ^= 0x80008000u; a.y ^= 0x80008000u; a.z ^= 0x80008000u; a.w ^= 0x80008000u;
 	b.x ^= 0x80008000u; b.y ^= 0x80008000u; b.z ^= 0x80008000u; b.w ^= 0x80008000u;
 	xs[0] = cvt_pair(a.x, b.x, 0x7610, sub);
@@ -204,171 +212,194 @@ __device__ __forceinline__ void fir_load_chunk(uint64_t *xs, const uint8_t *rowA
 	xs[7] = cvt_pair(a.w, b.w, 0x7632, sub);
 }
 
-/* one TMA request per stage: box = 64 rows x 148 uint32 (= 296 int16) of the planar sample matrix */
-__device__ __forceinline__ void tma_g2s_2d(void *dst, const CUtensorMap *tmap, int x, int y, uint64_t *bar)
+/* first stage of a tile (s == 0), whole warp: the row heads come from the carried history
+ * (4 zeros + 36 samples, generic stores made visible by the release of the arrive), the 256
+ * samples by 64 row copies that leave the heads alone */
+__device__ __noinline__ void fir_issue_first(uint8_t *dst, const int16_t *gbase, int64_t ch_stride, const ChanState *st_cg, int hist_sel,
+					      uint32_t bar, int lane)
 {
-	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-			     smem_u32(dst)),
-		     "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
-		     : "memory");
+	for (int i = lane; i < F_CH * F_HALO; i += 32) {
+		const int r = i / F_HALO, k = i % F_HALO;
+		const int16_t v = (k < F_HALO - GAIS_NTAPS) ? (int16_t) 0 : st_cg[r].hist[hist_sel][k - (F_HALO - GAIS_NTAPS)];
+		*reinterpret_cast<int16_t *>(dst + r * F_ROW_BYTES + k * 2) = v;
+	}
+	__syncwarp();
+	if (lane == 0)
+		mbar_expect_tx(bar, (uint32_t) (F_CH * F_T * 2));
+	__syncwarp();
+#pragma unroll
+	for (int h = 0; h < F_CH / 32; h++) {
+		const int r = lane + 32 * h;
+		bulk_g2s(smem_u32(dst) + r * F_ROW_BYTES + F_HALO * 2, gbase + (int64_t) r * ch_stride, F_T * 2, bar);
+	}
 }
 
-__global__ void __launch_bounds__(F_THREADS, 3)
+/* the tile ends in this stage: its last 36 samples (row index 260..295) are the next tile's history
+ * (src/filter.c:129-134); written to the other half of the double buffer */
+__device__ __noinline__ void fir_save_hist(const uint8_t *stage, ChanState *st_cg, int hist_next, int lane)
+{
+	for (int i = lane; i < F_CH * GAIS_NTAPS; i += 32) {
+		const int r = i / GAIS_NTAPS, k = i % GAIS_NTAPS;
+		st_cg[r].hist[hist_next][k] = *reinterpret_cast<const int16_t *>(stage + r * F_ROW_BYTES + (F_HALO + F_T - GAIS_NTAPS + k) * 2);
+	}
+}
+
+/*
+ * No producer warp: the loads of the first F_NSTAGE stages are issued by warp 0 before it starts
+ * computing; after that, the LAST warp to finish with a buffer (shared-memory arrival counter)
+ * issues the tensor-map request that refills it F_NSTAGE stages ahead.  Nobody polls.
+ */
+__global__ void __launch_bounds__(F_THREADS, F_MIN_BLOCKS)
 fir_sign_fast_kernel(const __grid_constant__ CUtensorMap tmap, const int16_t *__restrict__ base, int64_t ch_stride,
 		     ChanState *__restrict__ st, int hist_sel, int n_channels, int n_stages, int stages_per_block,
 		     uint32_t *__restrict__ signs, int dbg, int save_hist)
 {
 	extern __shared__ __align__(128) uint8_t tile[];
-	__shared__ __align__(8) uint64_t full_bar[F_NSTAGE], empty_bar[F_NSTAGE];
+	__shared__ __align__(8) uint64_t full_bar_[F_NSTAGE];
+	__shared__ uint32_t done_cnt_[F_NSTAGE];
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const int cg = blockIdx.x * F_CH;
 	const int s_begin = blockIdx.y * stages_per_block;
-	const int s_end = min(s_begin + stages_per_block, n_stages);
+	const int n_it = min(stages_per_block, n_stages - s_begin);
+	const uint32_t tile_a = smem_u32(tile), bar_a = smem_u32(full_bar_), cnt_a = smem_u32(done_cnt_);
 
 	if (tid == 0) {
+#pragma unroll
 		for (int i = 0; i < F_NSTAGE; i++) {
-			mbar_init(&full_bar[i], 1);
-			mbar_init(&empty_bar[i], F_CWARPS);
+			mbar_init(bar_a + 8 * i, 1);
+			done_cnt_[i] = 0;
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
 
-	if (warp == F_CWARPS) {
-		/* ===== producer warp: lane l brings rows l and l+32 of every stage ===== */
-		const int16_t *gbase = base + (int64_t) cg * ch_stride;
-		for (int s = s_begin; s < s_end; s++) {
-			const int it = s - s_begin, buf = it % F_NSTAGE;
-			if (it >= F_NSTAGE)
-				mbar_wait_sleep(&empty_bar[buf], (uint32_t) ((it / F_NSTAGE - 1) & 1));
-			uint8_t *dst = tile + buf * F_STAGE_BYTES;
-			const int64_t n0 = (int64_t) s * F_T;
-			if (s == 0) {
-				/* no samples before the run: rows start with 4 zeros + the 36 carried samples
-				 * (generic stores; made visible to the consumers by the release of the arrive below) */
-				for (int i = lane; i < F_CH * F_HALO; i += 32) {
-					const int r = i / F_HALO, k = i % F_HALO;
-					const int16_t v = (k < F_HALO - GAIS_NTAPS) ? (int16_t) 0 : st[cg + r].hist[hist_sel][k - (F_HALO - GAIS_NTAPS)];
-					*reinterpret_cast<int16_t *>(dst + r * F_ROW_BYTES + k * 2) = v;
-				}
-			}
-			__syncwarp();
-			if (dbg & 1) {          /* diagnostics only (GAIS_FIR_DBG=1): no loads, compute on stale smem */
-				if (lane == 0)
-					mbar_expect_tx(&full_bar[buf], 0);
-			} else if (s == 0) {
-				/* first stage of a tile: 64 row copies that leave the history bytes alone */
-				if (lane == 0)
-					mbar_expect_tx(&full_bar[buf], (uint32_t) (F_CH * F_T * 2));
-				__syncwarp();
-#pragma unroll
-				for (int h = 0; h < 2; h++) {
-					const int r = lane + 32 * h;
-					bulk_g2s(dst + r * F_ROW_BYTES + F_HALO * 2, gbase + (int64_t) r * ch_stride + n0, F_T * 2, &full_bar[buf]);
-				}
-			} else if (lane == 0) {
-				/* every other stage: ONE tensor-map request for the whole 64 x 296 box */
-				mbar_expect_tx(&full_bar[buf], (uint32_t) F_STAGE_BYTES);
-				tma_g2s_2d(dst, &tmap, (int) ((n0 - F_HALO) >> 1), cg, &full_bar[buf]);
+	if (warp == 0) {
+		for (int it = 0; it < F_NSTAGE && it < n_it; it++) {
+			const int s = s_begin + it;
+			if (s == 0)
+				fir_issue_first(tile + it * F_STAGE_BYTES, base + (int64_t) cg * ch_stride, ch_stride, st + cg, hist_sel,
+						bar_a + 8 * it, lane);
+			else if (lane == 0) {
+				mbar_expect_tx(bar_a + 8 * it, (uint32_t) F_STAGE_BYTES);
+				tma_g2s_2d(tile_a + it * F_STAGE_BYTES, &tmap, (s * F_T - F_HALO) >> 1, cg, bar_a + 8 * it);
 			}
 		}
-		return;
 	}
 
-	/* ===== consumer warps: warp w owns word column w; lane l channels l and l+32 ===== */
+	/* ===== every warp: word columns [F_W*warp, F_W*warp + F_W) of each stage; lane l channels l and l+32 ===== */
 	uint64_t T[6];      /* taps 12..17 (= 23..18), each in both halves */
 #pragma unroll
 	for (int k = 0; k < 6; k++)
 		T[k] = pack2(c_taps[12 + k], c_taps[12 + k]);
 	const uint64_t sub = pack2(F_MAGIC_SUB, F_MAGIC_SUB);
+	/* shared address of xs[0] of this lane's row A in buffer 0; output j uses xs[j+1 .. j+10] */
+	const uint32_t row0 = tile_a + lane * F_ROW_BYTES + (32 * F_W * warp + 16) * 2;
+	uint32_t *sp = signs + ((int64_t) s_begin * (F_T / 32) + F_W * warp) * n_channels + cg + lane;
+	const int64_t sp_step = (int64_t) (F_T / 32) * n_channels;
+	int tma_x = ((s_begin + F_NSTAGE) * F_T - F_HALO) >> 1;      /* of the next refill */
+	const bool saver = save_hist && s_begin + n_it == n_stages && warp == F_CWARPS - 1;
 
-	for (int s = s_begin; s < s_end; s++) {
-		const int it = s - s_begin, buf = it % F_NSTAGE;
-		mbar_wait(&full_bar[buf], (uint32_t) ((it / F_NSTAGE) & 1));
-		const uint8_t *stage = tile + buf * F_STAGE_BYTES;
-		const uint8_t *rowA = stage + lane * F_ROW_BYTES;
-		const uint8_t *rowB = stage + (lane + 32) * F_ROW_BYTES;
-		const int col0 = 32 * warp + 16;      /* row index of xs[0]; output j uses xs[j+1 .. j+10] */
-		if (dbg & 2) {          /* diagnostics only (GAIS_FIR_DBG=2): loads without compute */
-			__syncwarp();
-			if (lane == 0)
-				mbar_arrive(&empty_bar[buf]);
-			continue;
-		}
+	for (int it = 0; it < n_it; it++) {
+		const uint32_t buf = (uint32_t) it % F_NSTAGE;
+		if (!(dbg & 4) || it < F_NSTAGE)      /* GAIS_FIR_DBG=4 (diagnostics only): compute without refills */
+			mbar_wait(bar_a + 8 * buf, (uint32_t) ((it / F_NSTAGE) & 1));
+		const uint32_t rowA = row0 + buf * F_STAGE_BYTES;
+		const uint32_t rowB = rowA + 32 * F_ROW_BYTES;
+		uint32_t outA[F_W], outB[F_W];
 
-		uint64_t xs[48];
-		fir_load_chunk(xs + 0, rowA, rowB, (col0 + 0) * 2, sub);
-		fir_load_chunk(xs + 8, rowA, rowB, (col0 + 8) * 2, sub);
-
-		uint32_t wordA = 0, wordB = 0;        /* sign bits (1 = negative), first sample ends at the MSB */
-		uint32_t pendA = 0, pendB = 0;        /* outputs whose sign still needs the exact chain (bit j) */
+		if (!(dbg & 2)) {       /* GAIS_FIR_DBG=2 (diagnostics only): loads without compute */
+			uint64_t xs[16 + 32 * F_W];
+			fir_load_chunk(xs + 0, rowA, rowB, 0, sub);
+			fir_load_chunk(xs + 8, rowA, rowB, 16, sub);
 #pragma unroll
-		for (int g = 0; g < 4; g++) {
-			fir_load_chunk(xs + 8 * g + 16, rowA, rowB, (col0 + 8 * g + 16) * 2, sub);
-			uint64_t acc[8];
-			float m = 3.0e38f;
+			for (int wi = 0; wi < F_W; wi++) {
+				uint32_t wordA = 0, wordB = 0;        /* sign bits (1 = negative), first sample ends at the MSB */
+				uint32_t pendA = 0, pendB = 0;        /* outputs whose sign still needs tiers 2/3 (bit j) */
 #pragma unroll
-			for (int jj = 0; jj < 8; jj++) {
-				const int j = 8 * g + jj;
-				uint64_t a = fmul2(T[1], xs[j + 1]);
-				a = ffma2(T[2], xs[j + 2], a);
-				a = ffma2(T[3], xs[j + 3], a);
-				a = ffma2(T[4], xs[j + 4], a);
-				a = ffma2(T[5], xs[j + 5], a);
-				a = ffma2(T[5], xs[j + 6], a);
-				a = ffma2(T[4], xs[j + 7], a);
-				a = ffma2(T[3], xs[j + 8], a);
-				a = ffma2(T[2], xs[j + 9], a);
-				a = ffma2(T[1], xs[j + 10], a);
-				acc[jj] = a;
-				float ya, yb;
-				unpack2(a, ya, yb);
-				m = fminf(m, fminf(fabsf(ya), fabsf(yb)));
-				wordA = __funnelshift_l(__float_as_uint(ya), wordA, 1);
-				wordB = __funnelshift_l(__float_as_uint(yb), wordB, 1);
-			}
-			if (m <= F_E1) {
-				/* some of these 16 signs are in doubt: only MARK them here (the bits just shifted in for
-				 * them are placeholders).  They are settled after the column is done, by compact
-				 * out-of-line code, so the unrolled hot path stays small enough for the instruction cache */
+				for (int g4 = 0; g4 < 4; g4++) {
+					const int g = 4 * wi + g4;
+					fir_load_chunk(xs + 8 * g + 16, rowA, rowB, (8 * g + 16) * 2, sub);
+					uint64_t acc[8];
+					float m = 3.0e38f;
 #pragma unroll
-				for (int jj = 0; jj < 8; jj++) {
-					float ya, yb;
-					unpack2(acc[jj], ya, yb);
-					if (fabsf(ya) <= F_E1)
-						pendA |= 1u << (8 * g + jj);
-					if (fabsf(yb) <= F_E1)
-						pendB |= 1u << (8 * g + jj);
+					for (int jj = 0; jj < 8; jj++) {
+						const int j = 8 * g + jj;
+						uint64_t a = fmul2(T[1], xs[j + 1]);
+						a = ffma2(T[2], xs[j + 2], a);
+						a = ffma2(T[3], xs[j + 3], a);
+						a = ffma2(T[4], xs[j + 4], a);
+						a = ffma2(T[5], xs[j + 5], a);
+						a = ffma2(T[5], xs[j + 6], a);
+						a = ffma2(T[4], xs[j + 7], a);
+						a = ffma2(T[3], xs[j + 8], a);
+						a = ffma2(T[2], xs[j + 9], a);
+						a = ffma2(T[1], xs[j + 10], a);
+						acc[jj] = a;
+						float ya, yb;
+						unpack2(a, ya, yb);
+						m = fminf(m, fminf(fabsf(ya), fabsf(yb)));
+						wordA = __funnelshift_l(__float_as_uint(ya), wordA, 1);
+						wordB = __funnelshift_l(__float_as_uint(yb), wordB, 1);
+					}
+					if (m <= F_E1 && !(dbg & 16)) {      /* 16: diagnostics only, no guard marks */
+						/* some of these 16 signs are in doubt: only MARK them here (the bits just shifted in
+						 * for them are placeholders).  They are settled after the word is done, by compact
+						 * out-of-line code, so the unrolled hot path stays small enough for the instruction
+						 * cache */
+#pragma unroll
+						for (int jj = 0; jj < 8; jj++) {
+							float ya, yb;
+							unpack2(acc[jj], ya, yb);
+							if (fabsf(ya) <= F_E1)
+								pendA |= 1u << (8 * g4 + jj);
+							if (fabsf(yb) <= F_E1)
+								pendB |= 1u << (8 * g4 + jj);
+						}
+					}
 				}
+				/* device sign-word format: LSB first, bit j of word w = (filtered[32w + j] > 0) */
+				uint32_t oA = __brev(~wordA), oB = __brev(~wordB);
+				/* tiers 2 and 3: x[n-36] of output j of this word sits 12 samples before xs[0] + 32*wi + j */
+				const uint32_t wA = rowA + (32 * wi - 12) * 2;
+				if (dbg & 8)                  /* 8: diagnostics only, marks but no tier 2/3 */
+					pendA = pendB = 0;
+				while (pendA) {
+					const uint32_t j = (uint32_t) __ffs((int) pendA) - 1u;
+					pendA &= pendA - 1u;
+					oA = (oA & ~(1u << j)) | (fir_sign_resolve(wA + 2 * j) << j);
+				}
+				while (pendB) {
+					const uint32_t j = (uint32_t) __ffs((int) pendB) - 1u;
+					pendB &= pendB - 1u;
+					oB = (oB & ~(1u << j)) | (fir_sign_resolve(wA + 32 * F_ROW_BYTES + 2 * j) << j);
+				}
+				outA[wi] = oA;
+				outB[wi] = oB;
 			}
+		} else {
+#pragma unroll
+			for (int wi = 0; wi < F_W; wi++)
+				outA[wi] = outB[wi] = 0u;
 		}
-		/* device sign-word format: LSB first, bit j of word w = (filtered[32w + j] > 0) */
-		uint32_t outA = __brev(~wordA), outB = __brev(~wordB);
-		while (pendA | pendB) {      /* tiers 2 and 3: x[n-36] of output j sits at row index 32*warp + j + 4 */
-			const bool isA = pendA != 0u;
-			uint32_t &pend = isA ? pendA : pendB;
-			const int j = __ffs((int) pend) - 1;
-			pend &= pend - 1u;
-			const bool pos = fir_sign_resolve(reinterpret_cast<const int16_t *>(isA ? rowA : rowB) + 32 * warp + j + 4);
-			uint32_t &out = isA ? outA : outB;
-			out = (out & ~(1u << j)) | ((pos ? 1u : 0u) << j);
-		}
-		if (save_hist && s == n_stages - 1 && warp == F_CWARPS - 1) {
-			/* the tile ends here: its last 36 samples (row index 260..295) are the next tile's history
-			 * (src/filter.c:129-134); written to the other half of the double buffer */
-			for (int i = lane; i < F_CH * GAIS_NTAPS; i += 32) {
-				const int r = i / GAIS_NTAPS, k = i % GAIS_NTAPS;
-				st[cg + r].hist[hist_sel ^ 1][k] =
-					*reinterpret_cast<const int16_t *>(stage + r * F_ROW_BYTES + (F_HALO + F_T - GAIS_NTAPS + k) * 2);
-			}
-		}
+		if (saver && it == n_it - 1)
+			fir_save_hist(tile + buf * F_STAGE_BYTES, st + cg, hist_sel ^ 1, lane);
 		__syncwarp();
-		if (lane == 0)
-			mbar_arrive(&empty_bar[buf]);     /* this warp is done with the buffer */
-		const int64_t wrow = (int64_t) s * (F_T / 32) + warp;
-		signs[wrow * n_channels + cg + lane] = outA;
-		signs[wrow * n_channels + cg + lane + 32] = outB;
+		if (lane == 0) {
+			/* this warp is done with the buffer; the last one to say so refills it */
+			const uint32_t old = smem_add_acq_rel(cnt_a + 4 * buf, 1u);
+			if (old % F_CWARPS == F_CWARPS - 1 && it + F_NSTAGE < n_it && !(dbg & 4)) {
+				mbar_expect_tx(bar_a + 8 * buf, (uint32_t) F_STAGE_BYTES);
+				tma_g2s_2d(tile_a + buf * F_STAGE_BYTES, &tmap, tma_x, cg, bar_a + 8 * buf);
+			}
+		}
+		tma_x += F_T / 2;
+#pragma unroll
+		for (int wi = 0; wi < F_W; wi++) {
+			sp[(int64_t) wi * n_channels] = outA[wi];
+			sp[(int64_t) wi * n_channels + 32] = outB[wi];
+		}
+		sp += sp_step;
 	}
 }
 

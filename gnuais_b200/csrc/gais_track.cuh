@@ -310,29 +310,30 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 	const uint32_t zhi_start = zhi;
 	const int64_t run_start = (int64_t) zhi - (int64_t) out.run_bits[c];   /* stream index of the run's first bit */
 
-	const int64_t n_words = (n_frames + 31) >> 5;
+	const int n_words = (int) ((n_frames + 31) >> 5);                    /* a tile is far below 2^31 words */
+	const uint32_t last_nb = (uint32_t) (n_frames - 32 * (int64_t) (n_words - 1));   /* 1..32 samples in the last word */
 	const uint32_t *sp = signs + c;
 	uint32_t q[TRK_PREFETCH];
 #pragma unroll
 	for (int k = 0; k < TRK_PREFETCH; k++)
 		q[k] = (k < n_words) ? sp[(int64_t) k * n_channels] : 0u;
+	const uint32_t *pf = sp + (int64_t) TRK_PREFETCH * n_channels;      /* next word to prefetch */
 
-	for (int64_t w = 0; w < n_words; w++) {
+	for (int w = 0; w < n_words; w++, pf += n_channels) {
 		const uint32_t sw = q[0];
 #pragma unroll
 		for (int k = 0; k + 1 < TRK_PREFETCH; k++)
 			q[k] = q[k + 1];
-		q[TRK_PREFETCH - 1] = (w + TRK_PREFETCH < n_words) ? sp[(w + TRK_PREFETCH) * n_channels] : 0u;
-		const int64_t left = n_frames - w * 32;
-		const uint32_t nb = left < 32 ? (uint32_t) left : 32u;
+		q[TRK_PREFETCH - 1] = (w + TRK_PREFETCH < n_words) ? *pf : 0u;
 		/* LSB-first words: bit 0 is the first sample.  x marks samples whose sign differs from the
 		 * sample before */
 		uint32_t x = sw ^ __funnelshift_l(prevword, sw, 1);
-		if (nb < 32u) {
+		uint32_t nb = 32u;
+		prevword = sw;
+		if (w == n_words - 1 && last_nb < 32u) {      /* ragged end of the tile (warp-uniform) */
+			nb = last_nb;
 			x &= (1u << nb) - 1u;
 			prevword = sw << (32u - nb);
-		} else {
-			prevword = sw;
 		}
 		uint32_t jp = 0;
 		while (x) {
@@ -347,7 +348,10 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 			/* sample j changes sign: the pending NRZI difference bit flips, the phase is nudged
 			 * towards the crossing (src/receiver.c:113-119) before this sample's own increment */
 			dlo ^= 1u << (zhi - hb);
-			zlo += ((int32_t) zlo < 0) ? (0u - GAIS_NUDGE64) : GAIS_NUDGE64;
+			asm("{\n\t.reg .pred p;\n\t"
+			    "setp.lt.s32 p, %0, 0;\n\t"
+			    "add.u32 %0, %0, %1;\n\t"
+			    "@p sub.u32 %0, %0, %2;\n\t}" : "+r"(zlo) : "n"(GAIS_NUDGE64), "n"(2u * GAIS_NUDGE64));
 		}
 		{
 			unsigned long long Z = ((unsigned long long) zhi << 32) | zlo;

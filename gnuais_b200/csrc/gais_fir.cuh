@@ -249,7 +249,11 @@ __device__ __noinline__ void fir_save_hist(const uint8_t *stage, ChanState *st_c
  * computing; after that, the LAST warp to finish with a buffer (shared-memory arrival counter)
  * issues the tensor-map request that refills it F_NSTAGE stages ahead.  Nobody polls.
  */
+#ifdef F_MAXNREG
+__global__ void __maxnreg__(F_MAXNREG)
+#else
 __global__ void __launch_bounds__(F_THREADS, F_MIN_BLOCKS)
+#endif
 fir_sign_fast_kernel(const __grid_constant__ CUtensorMap tmap, const int16_t *__restrict__ base, int64_t ch_stride,
 		     ChanState *__restrict__ st, int hist_sel, int n_channels, int n_stages, int stages_per_block,
 		     uint32_t *__restrict__ signs, int dbg, int save_hist)

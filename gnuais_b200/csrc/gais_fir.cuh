@@ -7,29 +7,41 @@
  *
  * Fast kernel (sm_100a): "guard-banded" evaluation.
  *   tier 1   a10 = sum over the 10 centre taps 13..22 (packed fp32x2 FMAs, any rounding).
- *            |a10 - R| <= 0.4493 for ANY int16 input, R being the reference's rounded sum:
- *              0.1563  gamma_32 * sum|t_i x_i|   (reference's own rounding, sum t_i = 2.50001, |x| <= 32768)
- *              0.2444  2 * (t_12 + t_11 + ...) * 32768        (dropped taps)
- *              0.0488  10 roundings of the FMA chain
- *            so |a10| > E1 = 0.5  =>  sign(R) = sign(a10) and R != 0.
- *   tier 2   (only samples with |a10| <= E1, ~5e-4 of noisy audio) 12 taps 12..23, in registers,
- *            with a DATA-DEPENDENT bound: S12 = sum_{12 taps} t_i |x_i| is computed alongside and
+ *            |a10 - R| <= 0.3568 for ANY int16 input, R being the reference's rounded sum (u = 2^-24,
+ *            |x| <= 32768; a product t_i x_i that enters the reference's chain at position i is rounded
+ *            once by the multiply and once by each of the 34 - i additions that follow, so its relative
+ *            error is at most (35 - i) u; the first addition, 0 + p, is exact):
+ *              0.0855  32768 u * sum_i t_i (35 - i) = 32768 u * 43.7      (the reference's own rounding)
+ *              0.2444  2 * (t_12 + t_11 + ...) * 32768                    (dropped taps)
+ *              0.0269  32768 u * sum_k t_k (10 - k) = 32768 u * 13.8      (this kernel's 10-term FMA chain)
+ *            so |a10| > E1 = 0.36  =>  sign(R) = sign(a10) and R != 0.
+ *   tier 2   (only samples with |a10| <= E1, ~4e-4 of noisy audio) 12 taps 12..23, with a
+ *            DATA-DEPENDENT bound: S12 = sum_{12 taps} t_i |x_i| is computed alongside and
  *              |a12 - R| <= gamma_32 * (S12 + 0.001775) + 0.001775 + 12 u S12
- *                        <= 0.00355 + 2.64e-6 * S12          (u = 2^-24; 0.001775 = outer taps at full scale)
+ *                        <= 0.00355 + 2.64e-6 * S12          (0.001775 = outer taps at full scale)
  *            -> E2 = 0.004 + 3.0e-6 * S12 (0.006 on idle noise, 0.09 inside a burst).
  *   tier 3   (|a12| <= E2, ~1e-5 of samples) the exact 32-term chain, __fmul_rn/__fadd_rn in tap order.
  *
- * Data movement: one CTA = 64 channels x a run of 256-sample stages.  Each stage is 64 row
- * segments of (40 history + 256) int16 brought in by cp.async.bulk (TMA 1-D) into a
- * double-buffered shared-memory tile, completion on an mbarrier; every int16 is read from HBM
- * once (the 40-sample overlap of consecutive stages is an L2 hit).  Rows are padded to
- * 656 B (= 16 mod 128) so the 8 lanes of a quarter-warp, which read 8 DIFFERENT rows at the
- * same column, cover all 32 banks with their LDS.128.
+ * Data movement: one CTA = 64 channels x a run of 256-sample stages, 8 warps, no producer warp.
+ * Each stage is ONE 2-D tensor-map request (TMA, box 64 rows x (40 history + 256) int16) into a
+ * two-buffer shared-memory ring, completion on an mbarrier.  Warp 0 issues the first two requests;
+ * after that the LAST warp to finish with a buffer (shared-memory arrival counter, acq_rel) issues
+ * the request that refills it, so nobody polls.  Every int16 is read from HBM once (the 40-sample
+ * overlap of consecutive stages is an L2 hit).  Rows are 592 B (= 80 mod 128) so the 8 lanes of
+ * a quarter-warp, which read 8 DIFFERENT rows at the same column, hit 8 distinct 16-byte bank
+ * groups with their LDS.128.
  *
  * Work mapping: lane l of warp w computes the 32 outputs of word-column w for channels l and
- * l+32 of the group; the two channels ride in the two halves of fma.rn.f32x2 (SASS FFMA2: 2
- * MACs per issue slot on the heavy FMA pipe, profiles/r1_ubench_b200.txt).  Each lane ends with
- * two sign words that go to the [word][channel] buffer as two coalesced 128-byte warp stores.
+ * l+32 of the group; the two channels ride in the two halves of fma.rn.f32x2 (SASS FFMA2).
+ * Each lane ends with two sign words that go to the [word][channel] buffer as two coalesced
+ * 128-byte warp stores.
+ *
+ * What bounds it (tools/ubench_fir.cu, tools/ubench_ffma2.cu, profiles/r1_ubench_fir.txt): on B200
+ * an FFMA2 with three distinct operands occupies the dispatch port for ~2.3 cycles and does not
+ * share them with ALU-pipe work (PRMT/LOP3/SHF cost ~1.5 more cycles each next to it), so a word
+ * column costs ~1000 cycles per SM sub-partition whatever the order of the instructions: 320 FFMA2
+ * + 41 FADD2 (730), the int16 -> f32 conversion (180), the sign / guard bookkeeping (125).  The
+ * scalar-FFMA version of the same column is 11 % slower, the symmetric pre-add version 3 % slower.
  *
  * Device sign-word format: LSB first -- bit j of word w = (filtered[32w + j] > 0).
  */
@@ -59,7 +71,7 @@ constexpr int F_W = F_OUT_WORDS;
 constexpr int F_CWARPS = F_T / (32 * F_W);          /* warps of a CTA: each owns F_W word columns of a stage */
 constexpr int F_THREADS = F_CWARPS * 32;
 constexpr int F_STAGES_PER_BLOCK = 16;              /* 4096 samples of 64 channels per CTA */
-#define F_E1 0.5f
+#define F_E1 0.36f
 #define F_E2_BASE 0.004f       /* 2 * 0.001775 (taps <= 11 / >= 24 at full scale) rounded up */
 #define F_E2_SLOPE 3.0e-6f     /* (gamma_32 + 12 u) = 2.64e-6 rounded up */
 

@@ -225,6 +225,14 @@ def main():
            "gather_bytes": 0}
 
     pending = {"gather": None}
+    # how the decoded records reach rank 0: by default each rank copies its slice straight into rank 0's
+    # buffer over NVLink (CUDA IPC peer mapping, copy engines); GAIS_GATHER=nccl uses NCCL send/recv instead
+    gatherer, gather_kind = None, "none (one rank)"
+    if world > 1:
+        if os.environ.get("GAIS_GATHER", "peer") == "peer":
+            gatherer, gather_kind = gdist.PeerGather(dst=0), "NVLink peer copy into rank 0's buffer (CUDA IPC), counts + completion over NCCL"
+        else:
+            gather_kind = "NCCL point-to-point send/recv of exact-size record arrays, counts over NCCL"
 
     def step(timed: bool):
         rx.run(d, stream=stream.cuda_stream)
@@ -237,7 +245,7 @@ def main():
                 out = pending["gather"].wait()
                 if timed and out is not None:
                     acc["gather_bytes"] += int(out.numel())
-            pending["gather"] = gdist.gather_records_async(recs, dst=0)
+            pending["gather"] = gatherer.start(recs) if gatherer else gdist.gather_records_async(recs, dst=0)
         if timed:
             tm = rx.timing()
             for k in ("fir_ms", "track_ms", "post_ms", "total_ms"):
@@ -274,6 +282,8 @@ def main():
         dist.barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
+    if gatherer:
+        gatherer.close()
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -344,6 +354,7 @@ def main():
     }
     if world > 1:
         line["gather_bytes_per_step_rank0"] = acc["gather_bytes"] / args.steps
+        line["config"]["gather"] = gather_kind
 
     # ---- end to end through the C-ABI with HOST buffers (H2D + D2H inside the timed region) ----
     if not args.no_e2e:

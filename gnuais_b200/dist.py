@@ -125,3 +125,97 @@ def reduce_totals(totals, dst: int = 0, group=None, device="cpu"):
     t = torch.tensor(list(totals), dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return tuple(int(x) for x in t.cpu())
+
+
+class PeerGather:
+    """Collect every rank's records on `dst` WITHOUT a collective on the payload: `dst` owns a receive
+    buffer, every other rank maps it through CUDA IPC and copies its records straight into its slice
+    over NVLink with one cudaMemcpyAsync on a side stream (copy engines: no SMs, no NCCL proxy, so
+    the next step's kernels keep the GPU while the records move).  NCCL carries only the per-rank
+    counts (8 bytes each) and a one-word completion all-reduce.
+
+    One box only (CUDA IPC); needs the `cuda-python` bindings.  The buffer grows on demand: every rank
+    sees the same counts, so every rank takes the same (re)allocation branch.
+    """
+
+    def __init__(self, dst: int = 0, group=None):
+        from cuda.bindings import runtime as rt   # noqa: F401  (fail here, not in the middle of a step)
+
+        self._rt = rt
+        self.group, self.dst = group, dst
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.ptr, self.cap = 0, 0
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    @staticmethod
+    def _ck(res, what):
+        err = res[0] if isinstance(res, tuple) else res
+        if int(err) != 0:
+            raise RuntimeError(f"{what} failed: CUDA error {int(err)}")
+        return res[1] if isinstance(res, tuple) and len(res) > 1 else None
+
+    def _release(self):
+        rt = self._rt
+        if self.ptr:
+            torch.cuda.synchronize(self.device)
+            if self.rank == self.dst:
+                dist.barrier(group=self.group)          # nobody still has it mapped for writing
+                self._ck(rt.cudaFree(self.ptr), "cudaFree")
+            else:
+                self._ck(rt.cudaIpcCloseMemHandle(self.ptr), "cudaIpcCloseMemHandle")
+                dist.barrier(group=self.group)
+        self.ptr, self.cap = 0, 0
+
+    def _allocate(self, cap_records: int):
+        rt = self._rt
+        self._release()
+        nbytes = cap_records * REC_BYTES
+        blob = None
+        if self.rank == self.dst:
+            self.ptr = int(self._ck(rt.cudaMalloc(nbytes), "cudaMalloc"))
+            blob = bytes(self._ck(rt.cudaIpcGetMemHandle(self.ptr), "cudaIpcGetMemHandle").reserved)
+        box = [blob]
+        dist.broadcast_object_list(box, src=self.dst, group=self.group)
+        if self.rank != self.dst:
+            h = rt.cudaIpcMemHandle_t()
+            h.reserved = box[0]
+            self.ptr = int(self._ck(rt.cudaIpcOpenMemHandle(h, rt.cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle"))
+        self.cap = cap_records
+
+    def start(self, records: torch.Tensor) -> "PendingGather":
+        """Enqueue the collection of `records` ([n, 64] uint8, a private copy with global channel
+        numbers).  Returns at once; wait() gives the concatenation on dst (a view of the receive buffer,
+        valid until the next start()), None elsewhere."""
+        rt = self._rt
+        n_local = torch.tensor([records.shape[0]], dtype=torch.int64, device=self.device)
+        counts = torch.zeros(self.world, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(counts, n_local, group=self.group)
+        counts = counts.cpu().tolist()
+        offs = [0]
+        for c in counts:
+            offs.append(offs[-1] + c)
+        total = offs[-1]
+        if total > self.cap:
+            self._allocate(total + total // 4 + 1024)
+        records = records.contiguous()
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(ready)
+            if counts[self.rank] > 0:
+                self._ck(rt.cudaMemcpyAsync(self.ptr + offs[self.rank] * REC_BYTES, records.data_ptr(),
+                                            counts[self.rank] * REC_BYTES, rt.cudaMemcpyKind.cudaMemcpyDefault,
+                                            self.copy_stream.cuda_stream), "cudaMemcpyAsync (peer)")
+            # every rank enters this after its own copy has completed on its stream, so once it is
+            # done on dst all slices are in place
+            work = dist.all_reduce(self._flag, group=self.group, async_op=True)
+        out = None
+        if self.rank == self.dst:
+            out = (torch.as_tensor(_CudaView(self.ptr, total * REC_BYTES), device=self.device).view(total, REC_BYTES)
+                   if total else torch.empty((0, REC_BYTES), dtype=torch.uint8, device=self.device))
+        return PendingGather([work], out, records)
+
+    def close(self):
+        self._release()

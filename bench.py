@@ -9,7 +9,8 @@ message compaction) over one batch of synthetic GMSK int16 audio that is already
 HBM.  Workload at N GPUs: 65536 channels x 480000 samples (10 s at 48 kHz) PER GPU -- BASELINE
 config "65536 batched channels ... single B200" at N=1 and "524288 channels sharded across
 8xB200" at N=8 (weak scaling; channels are independent, no data-path collective; the only
-exchange is the NCCL collection of decoded-message buffers on rank 0, inside the timed step).
+exchange is the collection of decoded-message buffers on rank 0 -- NVLink peer copies into rank 0's
+buffer, counts and completion over NCCL -- inside the timed step).
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -227,12 +228,13 @@ def main():
     pending = {"gather": None}
     # how the decoded records reach rank 0: by default each rank copies its slice straight into rank 0's
     # buffer over NVLink (CUDA IPC peer mapping, copy engines); GAIS_GATHER=nccl uses NCCL send/recv instead
-    gatherer, gather_kind = None, "none (one rank)"
+    gx = {"peer": None, "kind": "none (one rank)"}
     if world > 1:
         if os.environ.get("GAIS_GATHER", "peer") == "peer":
-            gatherer, gather_kind = gdist.PeerGather(dst=0), "NVLink peer copy into rank 0's buffer (CUDA IPC), counts + completion over NCCL"
+            gx["peer"] = gdist.PeerGather(dst=0)
+            gx["kind"] = "NVLink peer copy into rank 0's buffer (CUDA IPC), counts + completion over NCCL"
         else:
-            gather_kind = "NCCL point-to-point send/recv of exact-size record arrays, counts over NCCL"
+            gx["kind"] = "NCCL point-to-point send/recv of exact-size record arrays, counts over NCCL"
 
     def step(timed: bool):
         rx.run(d, stream=stream.cuda_stream)
@@ -245,7 +247,14 @@ def main():
                 out = pending["gather"].wait()
                 if timed and out is not None:
                     acc["gather_bytes"] += int(out.numel())
-            pending["gather"] = gatherer.start(recs) if gatherer else gdist.gather_records_async(recs, dst=0)
+            if gx["peer"]:
+                try:
+                    pending["gather"] = gx["peer"].start(recs)
+                except gdist.PeerGatherUnavailable as e:      # raised on every rank together: switch transport
+                    gx["peer"], gx["kind"] = None, f"NCCL point-to-point send/recv (peer mapping unavailable: {e})"
+                    pending["gather"] = gdist.gather_records_async(recs, dst=0)
+            else:
+                pending["gather"] = gdist.gather_records_async(recs, dst=0)
         if timed:
             tm = rx.timing()
             for k in ("fir_ms", "track_ms", "post_ms", "total_ms"):
@@ -282,8 +291,8 @@ def main():
         dist.barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
-    if gatherer:
-        gatherer.close()
+    if gx["peer"]:
+        gx["peer"].close()
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -354,7 +363,7 @@ def main():
     }
     if world > 1:
         line["gather_bytes_per_step_rank0"] = acc["gather_bytes"] / args.steps
-        line["config"]["gather"] = gather_kind
+        line["config"]["gather"] = gx["kind"]
 
     # ---- end to end through the C-ABI with HOST buffers (H2D + D2H inside the timed region) ----
     if not args.no_e2e:

@@ -127,6 +127,10 @@ def reduce_totals(totals, dst: int = 0, group=None, device="cpu"):
     return tuple(int(x) for x in t.cpu())
 
 
+class PeerGatherUnavailable(RuntimeError):
+    """raised on EVERY rank of the group when the CUDA IPC mapping cannot be set up"""
+
+
 class PeerGather:
     """Collect every rank's records on `dst` WITHOUT a collective on the payload: `dst` owns a receive
     buffer, every other rank maps it through CUDA IPC and copies its records straight into its slice
@@ -178,10 +182,27 @@ class PeerGather:
             blob = bytes(self._ck(rt.cudaIpcGetMemHandle(self.ptr), "cudaIpcGetMemHandle").reserved)
         box = [blob]
         dist.broadcast_object_list(box, src=self.dst, group=self.group)
+        ok = 1
         if self.rank != self.dst:
             h = rt.cudaIpcMemHandle_t()
             h.reserved = box[0]
-            self.ptr = int(self._ck(rt.cudaIpcOpenMemHandle(h, rt.cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle"))
+            res = rt.cudaIpcOpenMemHandle(h, rt.cudaIpcMemLazyEnablePeerAccess)
+            if int(res[0]) == 0:
+                self.ptr = int(res[1])
+            else:
+                ok = 0
+        # the mapping either works on every rank or the whole group gives up together (no rank may be
+        # left waiting in a collective the others never enter)
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            if self.rank != self.dst and self.ptr:
+                rt.cudaIpcCloseMemHandle(self.ptr)
+            dist.barrier(group=self.group)               # every rank, whether its own mapping worked or not
+            if self.rank == self.dst:
+                rt.cudaFree(self.ptr)
+            self.ptr, self.cap = 0, 0
+            raise PeerGatherUnavailable("cudaIpcOpenMemHandle failed on at least one rank")
         self.cap = cap_records
 
     def start(self, records: torch.Tensor) -> "PendingGather":

@@ -378,14 +378,14 @@ def main():
         hv = host.numpy()
         d2h = 0
         for i in range(2):
-            rxe.run(hv); rxe.messages()
+            rxe.run(hv); rxe.messages(reuse=True)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         e_steps = max(3, min(args.steps, 5))
         for _ in range(e_steps):
             rxe.run(hv)
-            d2h += rxe.messages().nbytes
+            d2h += rxe.messages(reuse=True).nbytes      # D2H of the records into the receiver's page-locked buffer
         dt = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -394,7 +394,7 @@ def main():
         line["e2e"] = {"value": e_ch * frames * world * e_steps / dt / 1e6, "unit": UNIT,
                        "h2d_bytes_per_step": 2 * e_ch * frames, "d2h_bytes_per_step": d2h // e_steps,
                        "workload": f"{e_ch} channels/GPU x {frames} samples from pinned host memory through gais_run_host(), "
-                                   f"message records copied back every step", "steps": e_steps}
+                                   f"message records copied back to page-locked host memory every step", "steps": e_steps}
         cpu_src = hv
         rxe.close()
     else:

@@ -100,6 +100,8 @@ SYMBOLS = {
     "gais_sync": (C.c_int, [_P]),
     "gais_message_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "gais_get_messages": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "gais_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
+    "gais_host_free": (None, [_P]),
     "gais_device_messages": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "gais_get_nmea": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "gais_get_counters": (C.c_int, [_P, _P]),

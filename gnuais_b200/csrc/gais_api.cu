@@ -607,6 +607,25 @@ extern "C" int gais_get_messages(gais_ctx *ctx, gais_msg *h_out, int64_t cap, in
 	return 0;
 }
 
+extern "C" int gais_host_alloc(void **h_ptr, size_t bytes)
+{
+	if (!h_ptr)
+		return fail(GAIS_EINVAL, "null argument");
+	*h_ptr = NULL;
+	cudaError_t e = cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		return fail(e == cudaErrorMemoryAllocation ? GAIS_ENOMEM : GAIS_ECUDA, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+	}
+	return 0;
+}
+
+extern "C" void gais_host_free(void *h_ptr)
+{
+	if (h_ptr)
+		cudaFreeHost(h_ptr);
+}
+
 extern "C" int gais_get_nmea(gais_ctx *ctx, gais_nmea_rec *h_out, int64_t cap, int64_t *n_msgs)
 {
 	if (!ctx || !n_msgs)

@@ -35,6 +35,7 @@
 #ifndef GAIS_B200_H
 #define GAIS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -151,6 +152,11 @@ int gais_sync(gais_ctx *ctx);
 /* messages of the LAST run, dense, ordered by (channel, end_bit) */
 int gais_message_count(gais_ctx *ctx, int64_t *n_msgs);
 int gais_get_messages(gais_ctx *ctx, gais_msg *h_out, int64_t cap, int64_t *n_msgs);
+/* Page-locked host memory for the buffers handed to gais_run_host() / gais_get_messages(): copies to
+ * and from it run at PCIe speed without a staging pass (the reference reads its audio into a plain
+ * malloc'd buffer, src/ais.c:176-182; this is the batched equivalent of that allocation). */
+int gais_host_alloc(void **h_ptr, size_t bytes);
+void gais_host_free(void *h_ptr);
 /* device-resident view of the same array (for NCCL gathers / zero-copy consumers) */
 int gais_device_messages(gais_ctx *ctx, const gais_msg **d_msgs, int64_t *n_msgs);
 /* NMEA text of the last run's messages, armoured on the GPU; record i belongs to message i */

@@ -213,6 +213,14 @@ def test_host_buffers_equal_device_buffers():
     rx = BatchReceiver(7, 50000, layout="interleaved", tile_frames=4096)
     rx.run(x)
     res = dict(msgs=[rx.messages()], nmea_recs=[rx.nmea_records()], counters=rx.counters(), state=rx.state())
+    # the page-locked result buffer (what bench.py's e2e leg reads into) holds the same records, and is
+    # reused -- and regrown -- across runs
+    pinned = rx.messages(reuse=True)
+    assert pinned.tobytes() == res["msgs"][0].tobytes() and len(pinned) > 0
+    rx.reset()
+    rx.run(x[:20000])
+    again = rx.messages(reuse=True)
+    assert again.tobytes() == rx.messages().tobytes() and len(again) < len(res["msgs"][0])
     rx.close()
     for c in range(7):
         check_channel(res, c, O.port().run(np.ascontiguousarray(x[:, c])), bits=False, signs=False)

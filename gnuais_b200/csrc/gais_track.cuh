@@ -206,7 +206,9 @@ __device__ __forceinline__ uint32_t hdlc_chunk(HdlcRegs &f, const uint16_t *__re
 	 * out exactly */
 	bool fast = false;
 	uint32_t fast_id = 0;
-	if (f.id < 64u) {
+	/* (one vote first: with a single lane of the warp inside a frame the shortcut is off, and the
+	 * run-length test below -- ~50 instructions -- is not worth starting) */
+	if (__all_sync(__activemask(), f.id < 64u)) {
 		const uint32_t leak = f.id >> 5, nalt = (f.id >> 1) & 15u, last = f.id & 1u;
 		const uint32_t vm = (used >= 32u) ? 0xffffffffu : (1u << used) - 1u;
 		const uint32_t A = (W ^ ((W << 1) | last)) & vm;          /* bit i: b_i != b_(i-1) */

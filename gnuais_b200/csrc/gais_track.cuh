@@ -32,7 +32,7 @@
  * run-length test instead.
  *
  * A closed frame is NOT checked here: the stored bits go to the channel's slot list as a
- * 64-byte candidate and crc_kernel / finalize_kernel (massively parallel, no divergence) do
+ * 64-byte candidate and frame_check_kernel (one warp per channel, one lane per candidate) does
  * CRC, counters, seqnr and the in-place compaction into gais_msg records.  The reference's FSM
  * never looks at the CRC verdict (it resets either way, src/protodec.c:1113), so deferring it
  * changes nothing observable.
@@ -137,7 +137,7 @@ __host__ __device__ inline uint32_t hdlc_nibble_entry(uint32_t id, uint32_t v)
 }
 
 /* candidate layout (64 B, same slot a gais_msg will occupy): words 0..13 stored bits (LSB first),
- * word 14 = bufferpos | stop_bit << 16 (| status << 24 after crc_kernel), word 15 = closing bit index */
+ * word 14 = bufferpos | stop_bit << 16 , word 15 = closing bit index */
 /* everything by value: taking the address of the per-lane FSM registers would push them to local memory */
 __device__ __noinline__ uint32_t hdlc_emit(uint32_t pos, uint32_t shi, uint32_t b, uint32_t bit_index, const ChanState *s, int c,
 					   uint32_t ncand, gais_msg *slots, int slot_cap, int32_t *overflow)
@@ -393,9 +393,13 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 	out.run_bits[c] += zhi - zhi_start;
 }
 
-/* ---- frame check, fully parallel: one thread per candidate ------------------------------- */
+/* ---- frame check: one warp per channel, one lane per candidate ---------------------------------
+ * CRC-16 (src/protodec.c:106-167), the counters (src/protodec.c:1095-1115), the type gate and seqnr
+ * (src/protodec.c:896-929) and the in-place compaction of the CRC-ok candidates into gais_msg records.
+ * 32 candidates are checked at a time; their order-dependent parts -- the output position and the
+ * sequence number, which only advances on gated types -- are prefix counts over warp ballots. */
 __global__ void __launch_bounds__(256)
-crc_kernel(gais_msg *__restrict__ slots, const uint32_t *__restrict__ run_count, int slot_cap, int n_channels)
+frame_check_kernel(gais_msg *__restrict__ slots, uint32_t *__restrict__ run_count, int slot_cap, ChanState *st, int n_channels)
 {
 	__shared__ uint16_t table[256];
 	{
@@ -407,73 +411,73 @@ crc_kernel(gais_msg *__restrict__ slots, const uint32_t *__restrict__ run_count,
 		table[threadIdx.x] = (uint16_t) v;
 	}
 	__syncthreads();
-	const int64_t idx = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-	const int c = (int) (idx / slot_cap), k = (int) (idx % slot_cap);
-	if (c >= n_channels || (uint32_t) k >= run_count[c])
-		return;
-	uint32_t *w = reinterpret_cast<uint32_t *>(&slots[idx]);
-	const uint32_t meta = w[14];
-	const int pos = (int) (meta & 0xffffu), nbits = pos - 22;          /* src/protodec.c:1096 */
-	const uint32_t stopbit = (meta >> 16) & 1u;
-	uint32_t status = 2;                                               /* lostframes2 */
-	if (stopbit == 0u && nbits > 0) {
-		const int nbytes = (nbits >> 3) + 2;                           /* src/protodec.c:133-134 */
-		uint32_t crc = 0xffffu;
-		for (int j = 0; j < nbytes; j++) {
-			const uint32_t byte = (w[j >> 2] >> ((j & 3) * 8)) & 0xffu;
-			crc = (crc >> 8) ^ table[(crc ^ byte) & 0xffu];
-		}
-		status = ((~crc & 0xffffu) == 0x0f47u) ? 0u : 1u;              /* src/protodec.c:166 */
-	}
-	w[14] = meta | (status << 24);
-}
-
-/* one thread per channel: counters, type gate + seqnr (src/protodec.c:896-929), and in-place
- * compaction of the CRC-ok candidates into gais_msg records */
-__global__ void __launch_bounds__(128)
-finalize_kernel(gais_msg *__restrict__ slots, uint32_t *__restrict__ run_count, int slot_cap, ChanState *st, int n_channels)
-{
-	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	const int c = (int) (((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
 	if (c >= n_channels)
 		return;
 	const uint32_t ncand = run_count[c];
 	ChanState *s = &st[c];
-	int32_t ok = s->ok, crcfail = s->crcfail, sizefail = s->sizefail;
-	uint32_t seqnr = s->seqnr, nout = 0;
+	uint32_t seqnr = s->seqnr, nout = 0, n_ok = 0, n_crc = 0, n_size = 0;
 	uint4 *row = reinterpret_cast<uint4 *>(slots + (int64_t) c * slot_cap);
-	for (uint32_t k = 0; k < ncand; k++) {
-		uint4 q[4];
+	for (uint32_t base = 0; base < ncand; base += 32u) {
+		const uint32_t k = base + lane;
+		const bool valid = k < ncand;
+		uint32_t w[16];
+		if (valid) {
 #pragma unroll
-		for (int i = 0; i < 4; i++)
-			q[i] = row[4 * k + i];
-		const uint32_t meta = q[3].z, status = (meta >> 24) & 3u;
-		if (status == 1u) { crcfail++; continue; }
-		if (status == 2u) { sizefail++; continue; }
-		ok++;
-		uint32_t w[16] = { q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w,
-				   q[2].x, q[2].y, q[2].z, q[2].w, q[3].x, q[3].y, q[3].z, q[3].w };
-		const int nbits = (int) (meta & 0xffffu) - 22, nb = nbits >> 3;
-		const uint32_t type = (w[0] & 0xffu) >> 2;
-		const uint32_t gate = (type >= 1u && type <= 24u) ? 1u : 0u;
-		const uint32_t flags = seqnr | (gate << 4);
+			for (int i = 0; i < 4; i++) {
+				const uint4 q = row[4 * k + i];
+				w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
+			}
+		} else {
 #pragma unroll
-		for (int i = 0; i < 13; i++) {
-			const int lo = 32 * i;
-			if (8 * nb <= lo) w[i] = 0;
-			else if (8 * nb < lo + 32) w[i] &= (1u << (8 * nb - lo)) - 1u;
+			for (int i = 0; i < 16; i++)
+				w[i] = 0;
 		}
-		w[13] = ((nb > 52) ? (w[13] & 0xffu) : 0u) | (flags << 8) | ((uint32_t) nbits << 16);
-		w[14] = (uint32_t) c;
-		/* w[15] already holds the closing bit index */
-		if (gate)
-			seqnr = (seqnr + 1u) % 10u;                           /* src/protodec.c:924-926 */
+		const uint32_t meta = w[14];
+		const int nbits = (int) (meta & 0xffffu) - 22;                     /* src/protodec.c:1096 */
+		uint32_t status = valid ? 2u : 3u;                                  /* 2 = lostframes2 */
+		if (valid && ((meta >> 16) & 1u) == 0u && nbits > 0) {
+			const int nbytes = (nbits >> 3) + 2;                           /* src/protodec.c:133-134 */
+			uint32_t crc = 0xffffu;
+			for (int j = 0; j < nbytes; j++) {
+				const uint32_t byte = (w[j >> 2] >> ((j & 3) * 8)) & 0xffu;
+				crc = (crc >> 8) ^ table[(crc ^ byte) & 0xffu];
+			}
+			status = ((~crc & 0xffffu) == 0x0f47u) ? 0u : 1u;              /* src/protodec.c:166 */
+		}
+		const uint32_t type = (w[0] & 0xffu) >> 2;
+		const bool gate = status == 0u && type >= 1u && type <= 24u;
+		const uint32_t m_ok = __ballot_sync(0xffffffffu, status == 0u), m_crc = __ballot_sync(0xffffffffu, status == 1u);
+		const uint32_t m_size = __ballot_sync(0xffffffffu, status == 2u), m_gate = __ballot_sync(0xffffffffu, gate);
+		if (status == 0u) {
+			const uint32_t my_seq = (seqnr + (uint32_t) __popc(m_gate & lt)) % 10u;   /* src/protodec.c:924-926 */
+			const uint32_t my_out = nout + (uint32_t) __popc(m_ok & lt);
+			const int nb = nbits >> 3;
+			const uint32_t flags = my_seq | ((gate ? 1u : 0u) << 4);
 #pragma unroll
-		for (int i = 0; i < 4; i++)
-			row[4 * nout + i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-		nout++;
+			for (int i = 0; i < 13; i++) {
+				const int lo = 32 * i;
+				if (8 * nb <= lo) w[i] = 0;
+				else if (8 * nb < lo + 32) w[i] &= (1u << (8 * nb - lo)) - 1u;
+			}
+			w[13] = ((nb > 52) ? (w[13] & 0xffu) : 0u) | (flags << 8) | ((uint32_t) nbits << 16);
+			w[14] = (uint32_t) c;
+			/* w[15] already holds the closing bit index.  my_out <= k, and every candidate of this batch
+			 * is already in registers, so compacting in place cannot overwrite anything unread */
+#pragma unroll
+			for (int i = 0; i < 4; i++)
+				row[4 * my_out + i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+		}
+		nout += (uint32_t) __popc(m_ok);
+		seqnr = (seqnr + (uint32_t) __popc(m_gate)) % 10u;
+		n_ok += (uint32_t) __popc(m_ok); n_crc += (uint32_t) __popc(m_crc); n_size += (uint32_t) __popc(m_size);
 	}
-	s->ok = ok; s->crcfail = crcfail; s->sizefail = sizefail; s->seqnr = (uint8_t) seqnr;
-	run_count[c] = nout;
+	if (lane == 0u) {
+		s->ok += (int32_t) n_ok; s->crcfail += (int32_t) n_crc; s->sizefail += (int32_t) n_size;
+		s->seqnr = (uint8_t) seqnr;
+		run_count[c] = nout;
+	}
 }
 
 static inline int track_launch(const uint32_t *signs, ChanState *st, int n_ch, int64_t n_frames, const TrackOut &out,
@@ -486,10 +490,9 @@ static inline int track_launch(const uint32_t *signs, ChanState *st, int n_ch, i
 /* after the last tile of a run */
 static inline int finalize_launch(ChanState *st, int n_ch, const TrackOut &out, cudaStream_t stream)
 {
-	const int64_t total = (int64_t) n_ch * out.slot_cap;
-	crc_kernel<<<(unsigned) ((total + 255) / 256), 256, 0, stream>>>(out.slots, out.run_count, out.slot_cap, n_ch);
-	finalize_kernel<<<(n_ch + 127) / 128, 128, 0, stream>>>(out.slots, out.run_count, out.slot_cap, st, n_ch);
-	return cudaGetLastError() == cudaSuccess ? 2 : -1;
+	const int64_t threads = (int64_t) n_ch * 32;
+	frame_check_kernel<<<(unsigned) ((threads + 255) / 256), 256, 0, stream>>>(out.slots, out.run_count, out.slot_cap, st, n_ch);
+	return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 } /* namespace gais */

@@ -304,27 +304,29 @@ def main():
         total_msgs = acc["msgs"]
 
     tile_frames = rx_tile_frames(n_ch, args.tile_frames)
-    n_tiles = (frames + tile_frames - 1) // tile_frames
+    overlap = os.environ.get("GAIS_OVERLAP", "1") != "0" and frames > tile_frames
+    plan = rx_tile_plan(frames, tile_frames, overlap)       # samples per FIR / tracking launch, in order
+    n_tiles = len(plan)
     samples_per_step = n_ch * frames * world
     value = samples_per_step * args.steps / (ms * 1e-3) / 1e6
     totals = rx.totals()
 
     # ---- roofline of the dominant kernel (CUDA events inside the library, on the run's stream) ----
+    # the launches of a step are not all the same size (the last tile is shorter): achieved = the
+    # algorithmic bytes of ALL launches of the timed region over the sum of their durations
     peak, peak_src = measured_peak()
-    fir_avg = acc["fir_ms"] / (args.steps * n_tiles)
-    trk_avg = acc["track_ms"] / (args.steps * n_tiles)
-    dom = "fir_sign" if fir_avg >= trk_avg else "track"
-    launch_ms = max(fir_avg, trk_avg)
-    samples_per_launch = n_ch * min(tile_frames, frames) if n_tiles > 1 else n_ch * frames
-    msgs_per_launch = acc["msgs"] / (args.steps * n_tiles)
+    fir_step, trk_step = acc["fir_ms"] / args.steps, acc["track_ms"] / args.steps
+    dom = "fir_sign" if fir_step >= trk_step else "track"
+    step_ms_dom = max(fir_step, trk_step)
     # algorithmic bytes: 2 B per input sample for the kernel that reads the audio;
     # 64 B per emitted record belongs to the tracking kernel
-    alg_bytes = 2.0 * samples_per_launch if dom == "fir_sign" else 2.0 * samples_per_launch + 64.0 * msgs_per_launch
-    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
-    overlap = os.environ.get("GAIS_OVERLAP", "1") != "0" and n_tiles > 1
+    alg_step = 2.0 * n_ch * frames if dom == "fir_sign" else 2.0 * n_ch * frames + 64.0 * acc["msgs"] / args.steps
+    alg_bytes = alg_step / n_tiles
+    launch_ms = step_ms_dom / n_tiles
+    achieved = alg_step / (step_ms_dom * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(dom, alg_bytes), "peak_source": peak_src, "avg_launch_ms": launch_ms,
-                "alg_bytes_per_launch": alg_bytes,
+                "alg_bytes_per_launch": alg_bytes, "launches_per_step": n_tiles, "tile_plan_frames": plan_summary(plan),
                 "timing": "CUDA events on the stream each kernel is launched on, inside the timed region"
                           + ("; FIR of tile t+1 runs CONCURRENTLY with tracking of tile t, so both launch durations "
                              "include the other kernel's share of the SMs (see solo)" if overlap else ""),
@@ -343,10 +345,11 @@ def main():
                 tm = rxs.timing()
                 solo["fir_ms"] += tm["fir_ms"]; solo["track_ms"] += tm["track_ms"]
         rxs.close()
-        f_ms, t_ms = solo["fir_ms"] / (2 * n_tiles), solo["track_ms"] / (2 * n_tiles)
-        roofline["solo"] = {"fir_launch_ms": f_ms, "track_launch_ms": t_ms,
-                            "fir_GBps": 2.0 * samples_per_launch / (f_ms * 1e-3) / 1e9,
-                            "fir_frac": 2.0 * samples_per_launch / (f_ms * 1e-3) / 1e9 / peak}
+        n_plain = (frames + tile_frames - 1) // tile_frames      # overlap off: plain tiling
+        f_ms, t_ms = solo["fir_ms"] / (2 * n_plain), solo["track_ms"] / (2 * n_plain)
+        solo_gbps = 2.0 * n_ch * frames / (solo["fir_ms"] / 2 * 1e-3) / 1e9
+        roofline["solo"] = {"fir_launch_ms": f_ms, "track_launch_ms": t_ms, "launches_per_step": n_plain,
+                            "fir_GBps": solo_gbps, "fir_frac": solo_gbps / peak}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -415,6 +418,24 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def rx_tile_plan(frames: int, tile: int, overlap: bool):
+    """mirror of the library's time-tile plan (gais_api.cu gais_run_device): plain tiling.  (A plan with a
+    short first and last tile, meant to fill and drain the two-kernel pipeline faster, measured 0.6 %
+    slower and was dropped: profiles/r1_experiments.txt.)"""
+    return [min(tile, frames - f0) for f0 in range(0, frames, tile)]
+
+
+def plan_summary(plan):
+    out, i = [], 0
+    while i < len(plan):
+        j = i
+        while j < len(plan) and plan[j] == plan[i]:
+            j += 1
+        out.append(f"{j - i}x{plan[i]}" if j - i > 1 else str(plan[i]))
+        i = j
+    return " + ".join(out)
 
 
 def rx_tile_frames(n_ch: int, requested: int) -> int:

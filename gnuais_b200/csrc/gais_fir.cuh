@@ -64,6 +64,9 @@ constexpr int F_NSTAGE = 2;
 #ifndef F_OUT_WORDS
 #define F_OUT_WORDS 1                               /* sign words (32 outputs) per lane per stage */
 #endif
+#ifndef F_GUARD_GROUP
+#define F_GUARD_GROUP 4                            /* outputs per guard-band test (8, 4 or 2) */
+#endif
 #ifndef F_MIN_BLOCKS
 #define F_MIN_BLOCKS 3
 #endif
@@ -71,7 +74,9 @@ constexpr int F_W = F_OUT_WORDS;
 constexpr int F_CWARPS = F_T / (32 * F_W);          /* warps of a CTA: each owns F_W word columns of a stage */
 constexpr int F_THREADS = F_CWARPS * 32;
 constexpr int F_STAGES_PER_BLOCK = 16;              /* 4096 samples of 64 channels per CTA */
+#ifndef F_E1
 #define F_E1 0.36f
+#endif
 #define F_E2_BASE 0.004f       /* 2 * 0.001775 (taps <= 11 / >= 24 at full scale) rounded up */
 #define F_E2_SLOPE 3.0e-6f     /* (gamma_32 + 12 u) = 2.64e-6 rounded up */
 
@@ -121,11 +126,14 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr)
 	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
 	return v;
 }
+/* one int16 from shared memory as float, again without the conversion unit (an I2F holds the dispatch
+ * port for 8 cycles): the zero-extended halfword, biased and dropped into the mantissa of 2^23 + 2^22 by
+ * one XOR, minus 2^23 + 2^22 + 2^15 -- exact */
 __device__ __forceinline__ float lds_s16_f32(uint32_t addr)
 {
-	short v;
-	asm volatile("ld.shared.s16 %0, [%1];" : "=h"(v) : "r"(addr));
-	return (float) v;
+	unsigned short v;
+	asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+	return __fadd_rn(__uint_as_float((uint32_t) v ^ 0x4B408000u), -12615680.0f);
 }
 
 __device__ __forceinline__ uint64_t pack2(float lo, float hi)
@@ -261,6 +269,25 @@ __device__ __noinline__ void fir_save_hist(const uint8_t *stage, ChanState *st_c
  * computing; after that, the LAST warp to finish with a buffer (shared-memory arrival counter)
  * issues the tensor-map request that refills it F_NSTAGE stages ahead.  Nobody polls.
  */
+/* refill of one ring buffer, by the one lane that counted the last arrival (out of line: 1 stage in 8
+ * per warp takes it, and its ~20 instructions would otherwise be issued, predicated off, by every warp) */
+__device__ __noinline__ void fir_issue_refill(uint32_t bar, uint32_t dst, const CUtensorMap *tmap, int x, int y)
+{
+	mbar_expect_tx(bar, (uint32_t) F_STAGE_BYTES);
+	tma_g2s_2d(dst, tmap, x, y, bar);
+}
+
+/* a value the compiler must keep in a register instead of recomputing it from special registers */
+__device__ __forceinline__ uint32_t pinned_u32(uint32_t v)
+{
+	uint32_t r;
+	asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+	return r;
+}
+
+/* DBG: diagnostics only (GAIS_FIR_DBG, separate instantiations -- the product is DBG = 0):
+ * 2 loads without compute, 4 compute without refills, 8 guard marks but no tier 2/3, 16 no guard marks */
+template <int DBG>
 #ifdef F_MAXNREG
 __global__ void __maxnreg__(F_MAXNREG)
 #else
@@ -268,8 +295,9 @@ __global__ void __launch_bounds__(F_THREADS, F_MIN_BLOCKS)
 #endif
 fir_sign_fast_kernel(const __grid_constant__ CUtensorMap tmap, const int16_t *__restrict__ base, int64_t ch_stride,
 		     ChanState *__restrict__ st, int hist_sel, int n_channels, int n_stages, int stages_per_block,
-		     uint32_t *__restrict__ signs, int dbg, int save_hist)
+		     uint32_t *__restrict__ signs, int save_hist)
 {
+	constexpr int dbg = DBG;
 	extern __shared__ __align__(128) uint8_t tile[];
 	__shared__ __align__(8) uint64_t full_bar_[F_NSTAGE];
 	__shared__ uint32_t done_cnt_[F_NSTAGE];
@@ -278,7 +306,7 @@ fir_sign_fast_kernel(const __grid_constant__ CUtensorMap tmap, const int16_t *__
 	const int cg = blockIdx.x * F_CH;
 	const int s_begin = blockIdx.y * stages_per_block;
 	const int n_it = min(stages_per_block, n_stages - s_begin);
-	const uint32_t tile_a = smem_u32(tile), bar_a = smem_u32(full_bar_), cnt_a = smem_u32(done_cnt_);
+	const uint32_t tile_a = pinned_u32(smem_u32(tile)), bar_a = pinned_u32(smem_u32(full_bar_)), cnt_a = pinned_u32(smem_u32(done_cnt_));
 
 	if (tid == 0) {
 #pragma unroll
@@ -310,7 +338,7 @@ fir_sign_fast_kernel(const __grid_constant__ CUtensorMap tmap, const int16_t *__
 		T[k] = pack2(c_taps[12 + k], c_taps[12 + k]);
 	const uint64_t sub = pack2(F_MAGIC_SUB, F_MAGIC_SUB);
 	/* shared address of xs[0] of this lane's row A in buffer 0; output j uses xs[j+1 .. j+10] */
-	const uint32_t row0 = tile_a + lane * F_ROW_BYTES + (32 * F_W * warp + 16) * 2;
+	const uint32_t row0 = pinned_u32(tile_a + lane * F_ROW_BYTES + (32 * F_W * warp + 16) * 2);
 	uint32_t *sp = signs + ((int64_t) s_begin * (F_T / 32) + F_W * warp) * n_channels + cg + lane;
 	const int64_t sp_step = (int64_t) (F_T / 32) * n_channels;
 	int tma_x = ((s_begin + F_NSTAGE) * F_T - F_HALO) >> 1;      /* of the next refill */
@@ -336,41 +364,46 @@ fir_sign_fast_kernel(const __grid_constant__ CUtensorMap tmap, const int16_t *__
 				for (int g4 = 0; g4 < 4; g4++) {
 					const int g = 4 * wi + g4;
 					fir_load_chunk(xs + 8 * g + 16, rowA, rowB, (8 * g + 16) * 2, sub);
-					uint64_t acc[8];
-					float m = 3.0e38f;
 #pragma unroll
-					for (int jj = 0; jj < 8; jj++) {
-						const int j = 8 * g + jj;
-						uint64_t a = fmul2(T[1], xs[j + 1]);
-						a = ffma2(T[2], xs[j + 2], a);
-						a = ffma2(T[3], xs[j + 3], a);
-						a = ffma2(T[4], xs[j + 4], a);
-						a = ffma2(T[5], xs[j + 5], a);
-						a = ffma2(T[5], xs[j + 6], a);
-						a = ffma2(T[4], xs[j + 7], a);
-						a = ffma2(T[3], xs[j + 8], a);
-						a = ffma2(T[2], xs[j + 9], a);
-						a = ffma2(T[1], xs[j + 10], a);
-						acc[jj] = a;
-						float ya, yb;
-						unpack2(a, ya, yb);
-						m = fminf(m, fminf(fabsf(ya), fabsf(yb)));
-						wordA = __funnelshift_l(__float_as_uint(ya), wordA, 1);
-						wordB = __funnelshift_l(__float_as_uint(yb), wordB, 1);
-					}
-					if (m <= F_E1 && !(dbg & 16)) {      /* 16: diagnostics only, no guard marks */
-						/* some of these 16 signs are in doubt: only MARK them here (the bits just shifted in
-						 * for them are placeholders).  They are settled after the word is done, by compact
-						 * out-of-line code, so the unrolled hot path stays small enough for the instruction
-						 * cache */
+					for (int h = 0; h < 8 / F_GUARD_GROUP; h++) {
+						/* the guard test is made every F_GUARD_GROUP outputs: the accumulators have to stay in
+						 * registers until it is, and the kernel is short of registers */
+						uint64_t acc[F_GUARD_GROUP];
+						float m = 3.0e38f;
 #pragma unroll
-						for (int jj = 0; jj < 8; jj++) {
+						for (int jj = 0; jj < F_GUARD_GROUP; jj++) {
+							const int j = 8 * g + F_GUARD_GROUP * h + jj;
+							uint64_t a = fmul2(T[1], xs[j + 1]);
+							a = ffma2(T[2], xs[j + 2], a);
+							a = ffma2(T[3], xs[j + 3], a);
+							a = ffma2(T[4], xs[j + 4], a);
+							a = ffma2(T[5], xs[j + 5], a);
+							a = ffma2(T[5], xs[j + 6], a);
+							a = ffma2(T[4], xs[j + 7], a);
+							a = ffma2(T[3], xs[j + 8], a);
+							a = ffma2(T[2], xs[j + 9], a);
+							a = ffma2(T[1], xs[j + 10], a);
+							acc[jj] = a;
 							float ya, yb;
-							unpack2(acc[jj], ya, yb);
-							if (fabsf(ya) <= F_E1)
-								pendA |= 1u << (8 * g4 + jj);
-							if (fabsf(yb) <= F_E1)
-								pendB |= 1u << (8 * g4 + jj);
+							unpack2(a, ya, yb);
+							m = fminf(m, fminf(fabsf(ya), fabsf(yb)));
+							wordA = __funnelshift_l(__float_as_uint(ya), wordA, 1);
+							wordB = __funnelshift_l(__float_as_uint(yb), wordB, 1);
+						}
+						if (m <= F_E1 && !(dbg & 16)) {      /* 16: diagnostics only, no guard marks */
+							/* some of these signs are in doubt: only MARK them here (the bits just shifted in for
+							 * them are placeholders).  They are settled after the word is done, by compact
+							 * out-of-line code, so the unrolled hot path stays small enough for the instruction
+							 * cache */
+#pragma unroll
+							for (int jj = 0; jj < F_GUARD_GROUP; jj++) {
+								float ya, yb;
+								unpack2(acc[jj], ya, yb);
+								if (fabsf(ya) <= F_E1)
+									pendA |= 1u << (8 * g4 + F_GUARD_GROUP * h + jj);
+								if (fabsf(yb) <= F_E1)
+									pendB |= 1u << (8 * g4 + F_GUARD_GROUP * h + jj);
+							}
 						}
 					}
 				}
@@ -398,16 +431,12 @@ fir_sign_fast_kernel(const __grid_constant__ CUtensorMap tmap, const int16_t *__
 			for (int wi = 0; wi < F_W; wi++)
 				outA[wi] = outB[wi] = 0u;
 		}
-		if (saver && it == n_it - 1)
-			fir_save_hist(tile + buf * F_STAGE_BYTES, st + cg, hist_sel ^ 1, lane);
 		__syncwarp();
 		if (lane == 0) {
 			/* this warp is done with the buffer; the last one to say so refills it */
 			const uint32_t old = smem_add_acq_rel(cnt_a + 4 * buf, 1u);
-			if (old % F_CWARPS == F_CWARPS - 1 && it + F_NSTAGE < n_it && !(dbg & 4)) {
-				mbar_expect_tx(bar_a + 8 * buf, (uint32_t) F_STAGE_BYTES);
-				tma_g2s_2d(tile_a + buf * F_STAGE_BYTES, &tmap, tma_x, cg, bar_a + 8 * buf);
-			}
+			if (old % F_CWARPS == F_CWARPS - 1 && it + F_NSTAGE < n_it && !(dbg & 4))
+				fir_issue_refill(bar_a + 8 * buf, tile_a + buf * F_STAGE_BYTES, &tmap, tma_x, cg);
 		}
 		tma_x += F_T / 2;
 #pragma unroll
@@ -417,6 +446,10 @@ fir_sign_fast_kernel(const __grid_constant__ CUtensorMap tmap, const int16_t *__
 		}
 		sp += sp_step;
 	}
+	/* the tile ends in this CTA's last stage: its last 36 samples are the next tile's history.  Neither of
+	 * the last two buffers is refilled, so the stage is still there after the loop */
+	if (saver)
+		fir_save_hist(tile + ((n_it - 1) % F_NSTAGE) * F_STAGE_BYTES, st + cg, hist_sel ^ 1, lane);
 }
 
 /* cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda dependency */
@@ -424,7 +457,14 @@ static PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
 
 static inline int fir_setup(void)
 {
-	if (cudaFuncSetAttribute(fir_sign_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_NSTAGE * F_STAGE_BYTES) != cudaSuccess)
+	const int smem = F_NSTAGE * F_STAGE_BYTES;
+	if (cudaFuncSetAttribute(fir_sign_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+	    cudaFuncSetAttribute(fir_sign_fast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+	    cudaFuncSetAttribute(fir_sign_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+	    cudaFuncSetAttribute(fir_sign_fast_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+	    cudaFuncSetAttribute(fir_sign_fast_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+	    cudaFuncSetAttribute(fir_sign_fast_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+	    cudaFuncSetAttribute(fir_sign_fast_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
 		return -1;
 	if (!g_encode_tiled) {
 		void *fn = nullptr;
@@ -479,8 +519,18 @@ static inline int fir_launch(int fir_mode, int layout, SampleView view, ChanStat
 		CUtensorMap tm;
 		if (!fir_make_tmap(&tm, view.base, view.ch_stride, fast_ch, fast_frames))
 			return -1;
-		fir_sign_fast_kernel<<<grid, F_THREADS, F_NSTAGE * F_STAGE_BYTES, stream>>>(tm, view.base, view.ch_stride, st, hist_sel, n_ch,
-											     n_stages, spb, signs, dbg, fast_frames == n_frames ? 1 : 0);
+#define F_LAUNCH(D) fir_sign_fast_kernel<D><<<grid, F_THREADS, F_NSTAGE * F_STAGE_BYTES, stream>>>(tm, view.base, view.ch_stride, st, \
+		hist_sel, n_ch, n_stages, spb, signs, fast_frames == n_frames ? 1 : 0)
+		switch (dbg) {          /* 0 is the product; the others are the diagnostics of profiles/r1_experiments.txt */
+		case 2: F_LAUNCH(2); break;
+		case 4: F_LAUNCH(4); break;
+		case 6: F_LAUNCH(6); break;
+		case 8: F_LAUNCH(8); break;
+		case 16: F_LAUNCH(16); break;
+		case 20: F_LAUNCH(20); break;
+		default: F_LAUNCH(0); break;
+		}
+#undef F_LAUNCH
 		*hist_saved_channels = (fast_frames == n_frames) ? fast_ch : 0;
 		launches++;
 	} else {

@@ -302,15 +302,17 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 		return;
 	ChanState *s = &st[c];
 
-	uint32_t zlo = s->pll << 16, zhi = s->n_bits;
 	uint32_t prevword = (uint32_t) s->prev << 31;   /* bit 31 = sign of the last sample seen */
 	uint32_t dlo = s->dacc, nd = s->nd;             /* difference bits not yet given to the FSM */
-	uint32_t hb = zhi - nd;                         /* stream index of dlo bit 0 */
+	uint32_t hb = s->n_bits - nd;                   /* stream index of dlo bit 0 */
+	/* the phase register at sample 0 of the current word: DPLL phase in the lower half, slices since
+	 * the last hand-over (hb) in the upper half.  At sample j of the word it is zb + j * 13107 */
+	uint32_t zb = (nd << 16) | (s->pll & 0xffffu);
 	HdlcRegs f;
 	f.id = s->fsm; f.pos = s->pos; f.shi = s->cur; f.slo = s->cur2;
 	uint32_t ncand = out.run_count[c];
-	const uint32_t zhi_start = zhi;
-	const int64_t run_start = (int64_t) zhi - (int64_t) out.run_bits[c];   /* stream index of the run's first bit */
+	const uint32_t bits_start = hb + nd;
+	const int64_t run_start = (int64_t) bits_start - (int64_t) out.run_bits[c];   /* stream index of the run's first bit */
 
 	const int n_words = (int) ((n_frames + 31) >> 5);                    /* a tile is far below 2^31 words */
 	const uint32_t last_nb = (uint32_t) (n_frames - 32 * (int64_t) (n_words - 1));   /* 1..32 samples in the last word */
@@ -337,30 +339,21 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 			x &= (1u << nb) - 1u;
 			prevword = sw << (32u - nb);
 		}
-		uint32_t jp = 0;
 		while (x) {
 			const uint32_t iso = x & (0u - x);
 			const uint32_t j = 31u - (uint32_t) __clz((int) iso);
 			x ^= iso;
-			/* samples jp .. j-1: no sign change (src/receiver.c:121-134 only) */
-			unsigned long long Z = ((unsigned long long) zhi << 32) | zlo;
-			Z += (unsigned long long) (j - jp) * GAIS_INC64;
-			zlo = (uint32_t) Z; zhi = (uint32_t) (Z >> 32);
-			jp = j;
-			/* sample j changes sign: the pending NRZI difference bit flips, the phase is nudged
-			 * towards the crossing (src/receiver.c:113-119) before this sample's own increment */
-			dlo ^= 1u << (zhi - hb);
-			asm("{\n\t.reg .pred p;\n\t"
-			    "setp.lt.s32 p, %0, 0;\n\t"
-			    "add.u32 %0, %0, %1;\n\t"
-			    "@p sub.u32 %0, %0, %2;\n\t}" : "+r"(zlo) : "n"(GAIS_NUDGE64), "n"(2u * GAIS_NUDGE64));
+			/* samples 0 .. j-1 of the word: no sign change since the last one (src/receiver.c:121-134 only),
+			 * so the register at sample j is one 32-bit multiply-add away from the word's base */
+			const uint32_t zj = j * GAIS_PLL_INC + zb;
+			/* sample j changes sign: the pending NRZI difference bit flips, the phase is nudged towards the
+			 * crossing (src/receiver.c:113-119) before this sample's own increment.  The nudge goes into the
+			 * base: (zb + nudge) + j * 13107 = zj + nudge, which neither carries nor borrows */
+			dlo ^= 1u << (zj >> 16);
+			zb += (zj & 0x8000u) ? (0u - GAIS_PLL_NUDGE) : GAIS_PLL_NUDGE;
 		}
-		{
-			unsigned long long Z = ((unsigned long long) zhi << 32) | zlo;
-			Z += (unsigned long long) (nb - jp) * GAIS_INC64;
-			zlo = (uint32_t) Z; zhi = (uint32_t) (Z >> 32);
-		}
-		nd = zhi - hb;
+		zb += nb * GAIS_PLL_INC;                 /* base of the next word */
+		nd = zb >> 16;
 		if (nd >= 24u) {
 			/* at most 7 slices per 32 samples and at most 3 bits left over from the last hand-over,
 			 * so bit 31 of dlo is never reached before this point */
@@ -371,6 +364,7 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 			dlo >>= used;
 			hb += used;
 			nd -= used;
+			zb -= used << 16;
 		}
 	}
 	if (nd) {
@@ -382,15 +376,16 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 		hdlc_chunk(f, tab, ntab, W, nd, hb, true, s, c, ncand, out);
 		dlo >>= nd;
 		hb += nd;
+		zb -= nd << 16;
 		nd = 0;
 	}
 
-	s->pll = zlo >> 16; s->n_bits = zhi; s->prev = (uint8_t) (prevword >> 31);
+	s->pll = zb & 0xffffu; s->n_bits = hb + (zb >> 16); s->prev = (uint8_t) (prevword >> 31);
 	s->dacc = dlo; s->nd = (uint8_t) nd;
 	s->lastbit = (uint8_t) (((prevword >> 31) ^ (dlo >> nd)) & 1u);   /* sign at the last slice */
 	s->fsm = (uint8_t) f.id; s->pos = (uint16_t) f.pos; s->cur = f.shi; s->cur2 = f.slo;
 	out.run_count[c] = ncand;
-	out.run_bits[c] += zhi - zhi_start;
+	out.run_bits[c] += hb + (zb >> 16) - bits_start;
 }
 
 /* ---- frame check: one warp per channel, one lane per candidate ---------------------------------

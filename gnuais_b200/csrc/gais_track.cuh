@@ -118,10 +118,15 @@ struct HdlcRegs {
 	uint32_t shi, slo;  /* the last 64 stored bits, newest at bit 31 of shi */
 };
 
-/* nibble table entry: what four input bits do to state `id` (bit 0 of v first):
- *   bits 0..6 next id | 7..9 k = bits stored | 10..13 the stored bits (first at bit 10)
- *   | 14 ENTER (bufferpos = 0 before storing) | 15 EMIT (frame closed) | 16..17 position of the closing bit */
-constexpr uint32_t N_ENTER = 1u << 14, N_EMIT = 1u << 15;
+/* nibble table entry: what four input bits do to state `id` (bit 0 of v first).  The fields sit where the
+ * loop gets each of them with ONE instruction:
+ *   bits 0..1   position of the closing bit (EMIT only)
+ *   bits 6..12  next id << 6 = byte offset of the next state's row (16 entries x 4 B): the next lookup
+ *               address is (entry & 0x1fc0) | (nibble << 2)
+ *   bit 13 ENTER (bufferpos = 0 before storing) | bit 14 EMIT (frame closed)
+ *   byte 2      k = bits stored (0..4)
+ *   byte 3      the stored bits (first at bit 24) */
+constexpr uint32_t N_ROW = 0x1fc0u, N_ENTER = 1u << 13, N_EMIT = 1u << 14;
 
 __host__ __device__ inline uint32_t hdlc_nibble_entry(uint32_t id, uint32_t v)
 {
@@ -133,7 +138,7 @@ __host__ __device__ inline uint32_t hdlc_nibble_entry(uint32_t id, uint32_t v)
 		if (e & H_ENTER) { flags |= N_ENTER; k = 0; bits = 0; }
 		if (e & H_EMIT) { flags |= N_EMIT; p = i; }
 	}
-	return id | (k << 7) | (bits << 10) | flags | (p << 16);
+	return p | (id << 6) | flags | (k << 16) | (bits << 24);
 }
 
 /* candidate layout (64 B, same slot a gais_msg will occupy): words 0..13 stored bits (LSB first),
@@ -227,32 +232,40 @@ __device__ __forceinline__ uint32_t hdlc_chunk(HdlcRegs &f, const uint16_t *__re
 		f.id = fast_id;
 		return used;
 	}
+	/* the state travels through the loop as the byte offset of its table row; W2 = W << 2 puts nibble q at
+	 * bits 4q+2 .. 4q+5, where it is the entry index inside the row times 4 (the nibbles cover at most bits 0..27 of W) */
+	uint32_t row = f.id << 6;
+	const uint32_t W2 = W << 2;
+	const char *ntab_b = reinterpret_cast<const char *>(ntab);
 	for (uint32_t q = 0; q < nn; q++) {
-		const uint32_t v = (W >> (4u * q)) & 15u;
-		const uint32_t e = ntab[f.id * 16u + v];
-		const uint32_t k = (e >> 7) & 7u;
+		const uint32_t e = *reinterpret_cast<const uint32_t *>(ntab_b + (row | ((W2 >> (4u * q)) & 0x3cu)));
+		const uint32_t k = __byte_perm(e, 0u, 0x4442u);           /* byte 2 */
 		if (f.pos + k >= 449u && !(e & N_ENTER)) {
+			f.id = row >> 6;
 			const HdlcSerialRet r = hdlc_bits_serial(f, tab, W, 4u * q, 4u * q + 4u, hb, s, c, ncand, out.slots, out.slot_cap,
 								 out.overflow);   /* rare: frame outgrows the buffer */
 			f = r.f;
 			ncand = r.ncand;
+			row = f.id << 6;
 			continue;
 		}
 		if (e & N_ENTER)
 			f.pos = 0;
-		f.id = e & 0x7fu;
-		const uint32_t bits = (e >> 10) & 15u, pos2 = f.pos + k;
+		row = e & N_ROW;
+		const uint32_t bits = e >> 24, pos2 = f.pos + k;
 		f.slo = __funnelshift_r(f.slo, f.shi, k);                 /* append k bits at the top of shi:slo */
 		f.shi = __funnelshift_r(f.shi, bits, k);
 		if ((f.pos ^ pos2) & 32u)                                 /* a 32-bit word of the frame is complete */
 			s->store[(pos2 >> 5) - 1u] = __funnelshift_rc(f.slo, f.shi, 32u - (pos2 & 31u));
 		f.pos = pos2;
 		if (e & N_EMIT) {
-			const uint32_t p = (e >> 16) & 3u;
-			ncand = hdlc_emit(f.pos, f.shi, (v >> p) & 1u, hb + 4u * q + p, s, c, ncand, out.slots, out.slot_cap, out.overflow);
+			const uint32_t p = e & 3u;
+			ncand = hdlc_emit(f.pos, f.shi, (W >> (4u * q + p)) & 1u, hb + 4u * q + p, s, c, ncand, out.slots, out.slot_cap,
+					  out.overflow);
 			f.pos = 0;
 		}
 	}
+	f.id = row >> 6;
 	if (tail && used > nn * 4u) {
 		const HdlcSerialRet r = hdlc_bits_serial(f, tab, W, nn * 4u, used, hb, s, c, ncand, out.slots, out.slot_cap, out.overflow);
 		f = r.f;

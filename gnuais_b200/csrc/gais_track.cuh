@@ -294,10 +294,31 @@ __device__ __forceinline__ void bits_or(const TrackOut &out, int c, int64_t off,
 }
 
 constexpr int TRK_THREADS = 128;
-constexpr int TRK_PREFETCH = 4;          /* sign words loaded ahead of use (L2 latency) */
+#ifndef TRK_PREFETCH_DEPTH
+#define TRK_PREFETCH_DEPTH 2
+#endif
+constexpr int TRK_PREFETCH = TRK_PREFETCH_DEPTH;   /* sign words loaded ahead of use: a word takes a warp ~1700 cycles, an L2 hit ~700 */
 #ifndef TRK_MIN_BLOCKS
 #define TRK_MIN_BLOCKS 1
 #endif
+
+/* the sign changes of one word (bit j of x: sample j differs from the sample before it), in time order */
+__device__ __forceinline__ void dpll_word(uint32_t x, uint32_t &zb, uint32_t &dlo)
+{
+	while (x) {
+		const uint32_t iso = x & (0u - x);
+		const uint32_t j = 31u - (uint32_t) __clz((int) iso);
+		x ^= iso;
+		/* samples 0 .. j-1 of the word: no sign change since the last one (src/receiver.c:121-134 only),
+		 * so the register at sample j is one 32-bit multiply-add away from the word's base */
+		const uint32_t zj = j * GAIS_PLL_INC + zb;
+		/* sample j changes sign: the pending NRZI difference bit flips, the phase is nudged towards the
+		 * crossing (src/receiver.c:113-119) before this sample's own increment.  The nudge goes into the
+		 * base: (zb + nudge) + j * 13107 = zj + nudge, which neither carries nor borrows */
+		dlo ^= 1u << (zj >> 16);
+		zb += (zj & 0x8000u) ? (0u - GAIS_PLL_NUDGE) : GAIS_PLL_NUDGE;
+	}
+}
 
 __global__ void __launch_bounds__(TRK_THREADS, TRK_MIN_BLOCKS)
 track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, int64_t n_frames, TrackOut out)
@@ -328,7 +349,6 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 	const int64_t run_start = (int64_t) bits_start - (int64_t) out.run_bits[c];   /* stream index of the run's first bit */
 
 	const int n_words = (int) ((n_frames + 31) >> 5);                    /* a tile is far below 2^31 words */
-	const uint32_t last_nb = (uint32_t) (n_frames - 32 * (int64_t) (n_words - 1));   /* 1..32 samples in the last word */
 	const uint32_t *sp = signs + c;
 	uint32_t q[TRK_PREFETCH];
 #pragma unroll
@@ -336,7 +356,8 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 		q[k] = (k < n_words) ? sp[(int64_t) k * n_channels] : 0u;
 	const uint32_t *pf = sp + (int64_t) TRK_PREFETCH * n_channels;      /* next word to prefetch */
 
-	for (int w = 0; w < n_words; w++, pf += n_channels) {
+	const int n_full = (int) (n_frames >> 5);          /* whole 32-sample words; a ragged end comes after the loop */
+	for (int w = 0; w < n_full; w++, pf += n_channels) {
 		const uint32_t sw = q[0];
 #pragma unroll
 		for (int k = 0; k + 1 < TRK_PREFETCH; k++)
@@ -344,28 +365,10 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 		q[TRK_PREFETCH - 1] = (w + TRK_PREFETCH < n_words) ? *pf : 0u;
 		/* LSB-first words: bit 0 is the first sample.  x marks samples whose sign differs from the
 		 * sample before */
-		uint32_t x = sw ^ __funnelshift_l(prevword, sw, 1);
-		uint32_t nb = 32u;
+		const uint32_t x = sw ^ __funnelshift_l(prevword, sw, 1);
 		prevword = sw;
-		if (w == n_words - 1 && last_nb < 32u) {      /* ragged end of the tile (warp-uniform) */
-			nb = last_nb;
-			x &= (1u << nb) - 1u;
-			prevword = sw << (32u - nb);
-		}
-		while (x) {
-			const uint32_t iso = x & (0u - x);
-			const uint32_t j = 31u - (uint32_t) __clz((int) iso);
-			x ^= iso;
-			/* samples 0 .. j-1 of the word: no sign change since the last one (src/receiver.c:121-134 only),
-			 * so the register at sample j is one 32-bit multiply-add away from the word's base */
-			const uint32_t zj = j * GAIS_PLL_INC + zb;
-			/* sample j changes sign: the pending NRZI difference bit flips, the phase is nudged towards the
-			 * crossing (src/receiver.c:113-119) before this sample's own increment.  The nudge goes into the
-			 * base: (zb + nudge) + j * 13107 = zj + nudge, which neither carries nor borrows */
-			dlo ^= 1u << (zj >> 16);
-			zb += (zj & 0x8000u) ? (0u - GAIS_PLL_NUDGE) : GAIS_PLL_NUDGE;
-		}
-		zb += nb * GAIS_PLL_INC;                 /* base of the next word */
+		dpll_word(x, zb, dlo);
+		zb += 32u * GAIS_PLL_INC;                /* base of the next word */
 		nd = zb >> 16;
 		if (nd >= 24u) {
 			/* at most 7 slices per 32 samples and at most 3 bits left over from the last hand-over,
@@ -379,6 +382,16 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 			nd -= used;
 			zb -= used << 16;
 		}
+	}
+	if (n_frames & 31) {
+		/* ragged end of the tile: the last word holds 1..31 samples.  What it slices is handed over by the
+		 * flush below (at most 23 + 7 bits are pending, dlo has room for them) */
+		const uint32_t nb = (uint32_t) (n_frames & 31), sw = q[0];
+		const uint32_t x = (sw ^ __funnelshift_l(prevword, sw, 1)) & ((1u << nb) - 1u);
+		prevword = sw << (32u - nb);
+		dpll_word(x, zb, dlo);
+		zb += nb * GAIS_PLL_INC;
+		nd = zb >> 16;
 	}
 	if (nd) {
 		/* end of the tile: hand ALL sliced bits over now, so that FSM state, candidates and

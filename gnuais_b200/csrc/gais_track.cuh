@@ -293,7 +293,10 @@ __device__ __forceinline__ void bits_or(const TrackOut &out, int c, int64_t off,
 		row[(off >> 5) + 1] |= W >> (32u - sh);
 }
 
-constexpr int TRK_THREADS = 128;
+#ifndef TRK_BLOCK
+#define TRK_BLOCK 128
+#endif
+constexpr int TRK_THREADS = TRK_BLOCK;
 #ifndef TRK_PREFETCH_DEPTH
 #define TRK_PREFETCH_DEPTH 2
 #endif

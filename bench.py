@@ -442,7 +442,7 @@ def rx_tile_frames(n_ch: int, requested: int) -> int:
     """mirror of the library's default time-tile choice (gais_api.cu gais_create)"""
     tile = requested or int(os.environ.get("GAIS_TILE_FRAMES", "0") or 0)
     if tile <= 0:
-        tile = 256 * 1024 * 1024 * 8 // n_ch
+        tile = 384 * 1024 * 1024 * 8 // n_ch
         tile = max(2048, min(65536, tile))
     return (tile + 1023) // 1024 * 1024
 

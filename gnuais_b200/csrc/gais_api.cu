@@ -217,11 +217,12 @@ extern "C" int gais_create(const gais_config *cfg, gais_ctx **out)
 	if (cfg->reserved[1] > 0)
 		tile = cfg->reserved[1];
 	if (tile <= 0) {
-		/* default: 256 MB of sign words per tile (n_ch * tile / 8 bytes).  Measured on B200
-		 * (profiles/r1_sweep_tiles.txt): fewer, longer launches beat keeping the sign words inside
-		 * the 126 MB L2 -- the extra 1/16 byte per sample of HBM traffic is cheaper than the
-		 * per-launch ramp of 2 x 117 kernels */
-		tile = (int64_t) 256 * 1024 * 1024 * 8 / ctx->n_ch;
+		/* default: 384 MB of sign words per tile (n_ch * tile / 8 bytes).  Measured on B200
+		 * (profiles/r1_sweep_tiles.txt, profiles/r1_experiments.txt): fewer, longer launches beat keeping
+		 * the sign words inside the 126 MB L2 -- the extra 1/16 byte per sample of HBM traffic is cheaper
+		 * than the per-launch ramps; with the final kernels 49152-sample tiles at 65536 channels are
+		 * 1.8 % faster than 32768 and than 61440 */
+		tile = (int64_t) 384 * 1024 * 1024 * 8 / ctx->n_ch;
 		if (tile > 65536) tile = 65536;
 		if (tile < 2048) tile = 2048;
 	}

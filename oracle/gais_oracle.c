@@ -383,6 +383,27 @@ struct bench_arg {
 	int64_t ok;
 };
 
+/* test hook: the HDLC bit machine alone -- fsm_bit() fed with NRZI-decoded bits (one per byte) from the
+ * reset state.  stats = {ok, crcfail, sizefail}; frames as in goracle_run().  Lets the tests compare the GPU
+ * path's state tables with this FSM without going through audio. */
+int goracle_fsm_bits(const uint8_t *bits, int64_t n_bits, int32_t stats[3], goracle_frame *frames, int64_t frames_cap,
+		     int64_t *n_frames_out)
+{
+	chan_t *c = (chan_t *) malloc(sizeof(chan_t));
+	if (!c)
+		return -1;
+	chan_init(c);
+	c->frames = frames;
+	c->frames_cap = frames_cap;
+	for (int64_t i = 0; i < n_bits; i++)
+		fsm_bit(c, bits[i] & 1);
+	stats[0] = c->ok; stats[1] = c->crcfail; stats[2] = c->sizefail;
+	if (n_frames_out)
+		*n_frames_out = c->n_frames;
+	free(c);
+	return 0;
+}
+
 static void *bench_thread(void *p)
 {
 	struct bench_arg *a = (struct bench_arg *) p;

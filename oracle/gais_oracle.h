@@ -51,6 +51,9 @@ int goracle_nmea(const uint8_t *payload, int nbits, uint8_t *seqnr, char *out);
 
 /* CRC-16/X.25 as protodec_sdlc_crc(): returns ~crc; a good frame+FCS gives 0x0f47 */
 uint16_t goracle_crc16(const uint8_t *data, unsigned len);
+/* the HDLC bit machine alone, fed with NRZI-decoded bits (one per byte) from the reset state */
+int goracle_fsm_bits(const uint8_t *bits, int64_t n_bits, int32_t stats[3], goracle_frame *frames, int64_t frames_cap,
+		     int64_t *n_frames_out);
 
 /* float32 bit patterns of the 36 taps as the reference's compiler rounds them */
 const uint32_t *goracle_tap_bits(void);

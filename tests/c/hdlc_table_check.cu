@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <vector>
 #include "gais_track.cuh"
+#include "gais_oracle.h"
 
 using namespace gais;
 
@@ -30,7 +31,26 @@ int main()
 		for (int i = 0; i < train; i++) bits.push_back(i & 1);
 		const int flag[8] = { 0, 1, 1, 1, 1, 1, 1, 0 };
 		for (int i = 0; i < 8; i++) bits.push_back(flag[i]);
-		int len = rnd() % 470, ones = 0;
+		int ones = 0;
+		if (burst % 3 == 0) {
+			// a well-formed frame: 21 or 53 payload bytes + CRC-16/X.25 (low byte first), LSB first, bit-stuffed
+			uint8_t bytes[55];
+			const int nb = (burst % 6 == 0) ? 53 : 21;
+			for (int j = 0; j < nb; j++) bytes[j] = (uint8_t) rnd();
+			const uint16_t fcs = goracle_crc16(bytes, (unsigned) nb);
+			bytes[nb] = (uint8_t) (fcs & 0xff);
+			bytes[nb + 1] = (uint8_t) (fcs >> 8);
+			for (int j = 0; j < nb + 2; j++)
+				for (int k = 0; k < 8; k++) {
+					const int b = (bytes[j] >> k) & 1;
+					bits.push_back(b);
+					ones = b ? ones + 1 : 0;
+					if (ones == 5) { bits.push_back(0); ones = 0; }
+				}
+			for (int i = 0; i < 8; i++) bits.push_back(flag[i]);
+			continue;
+		}
+		int len = rnd() % 470;
 		for (int i = 0; i < len; i++) {
 			int b = (rnd() % 3) != 0;            // biased to ones: exercises the stuffing paths
 			bits.push_back(b);
@@ -100,6 +120,61 @@ int main()
 		for (size_t f = 0; f < fa.size(); f++)
 			if (fa[f] != fb[f]) { printf("frame %zu differs (%zu / %zu bits)\n", f, fa[f].size(), fb[f].size()); return 1; }
 		printf("ok: %zu bits, %zu frames, %d start states\n", bits.size(), fa.size(), H_NSTATES);
+	}
+	// against the oracle's bit machine (oracle/gais_oracle.c fsm_bit(), pinned to the reference): the table
+	// FSM with the kernel's buffer rules (position reset on ENTER / EMIT, reset at 449 stored bits, a closed
+	// frame judged by stop bit, length and CRC) must report the same frame events
+	{
+		std::vector<uint8_t> b8(bits.begin(), bits.end());
+		std::vector<goracle_frame> want(100000);
+		int32_t stats[3];
+		int64_t n_want = 0;
+		if (goracle_fsm_bits(b8.data(), (int64_t) b8.size(), stats, want.data(), (int64_t) want.size(), &n_want) != 0) return 1;
+		uint32_t id = hdlc_hunt_id(0, 0, 0), pos = 0;
+		uint8_t store[450] = { 0 };
+		int64_t n_got = 0;
+		int32_t got_stats[3] = { 0, 0, 0 };
+		for (size_t i = 0; i < bits.size(); i++) {
+			const uint32_t bit = (uint32_t) bits[i], e = hdlc_transition(id, bit);
+			id = e & 0x7fu;
+			if (e & H_STORE) {                                   // as hdlc_bits_serial() in gais_track.cuh
+				store[pos++] = (uint8_t) bit;
+				if (pos >= 449u) { id = hdlc_hunt_id(0, 0, bit); pos = 0; }
+			}
+			if (e & H_ENTER) { pos = 0; for (int k = 0; k < 450; k++) store[k] = 0; }
+			if (e & H_EMIT) {
+				const int nbits = (int) pos - 22;
+				int status = 2;
+				if (bit == 0 && nbits > 0) {                     // as frame_check_kernel
+					uint8_t bytes[60];
+					const int nb = nbits / 8;
+					for (int j = 0; j < nb + 2; j++) {
+						unsigned v = 0;
+						for (int k = 0; k < 8; k++) v |= (unsigned) store[8 * j + k] << k;
+						bytes[j] = (uint8_t) v;
+					}
+					status = goracle_crc16(bytes, (unsigned) nb + 2) == 0x0f47 ? 0 : 1;
+				}
+				got_stats[status]++;
+				if (n_got < n_want) {
+					const goracle_frame &w = want[n_got];
+					if (w.end_bit != (uint32_t) i || w.nbits != (int16_t) nbits || w.status != status) {
+						printf("frame %lld: end %u/%zu nbits %d/%d status %d/%d\n", (long long) n_got, w.end_bit, i, w.nbits, nbits, w.status,
+						       status);
+						return 1;
+					}
+				}
+				n_got++;
+				pos = 0;
+			}
+		}
+		if (n_got != n_want || got_stats[0] != stats[0] || got_stats[1] != stats[1] || got_stats[2] != stats[2] || n_got < 1000) {
+			printf("oracle: %lld frames (%d/%d/%d), tables: %lld (%d/%d/%d)\n", (long long) n_want, stats[0], stats[1], stats[2],
+			       (long long) n_got, got_stats[0], got_stats[1], got_stats[2]);
+			return 1;
+		}
+		printf("ok: %lld frame events equal to the oracle's (%d crc-ok, %d crc-fail, %d size-fail)\n", (long long) n_got, stats[0], stats[1],
+		       stats[2]);
 	}
 	return 0;
 }

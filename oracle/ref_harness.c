@@ -149,6 +149,33 @@ int64_t gref_getdata_text(const uint8_t *payload, int nbits, int seqnr, char cha
 }
 
 /*
+ * The reference's HDLC bit machine alone: protodec_initialize() + protodec_decode() (src/protodec.c:988-1122)
+ * over NRZI-decoded bits, one per byte, as receiver_run() hands them over (src/receiver.c:126-131).
+ * stats[3] = { receivedframes, lostframes, lostframes2 }.  The NMEA the decoder emits goes to `nmea_fd`
+ * (a serial_state_t on that descriptor), -1 for none.
+ */
+int gref_fsm_bits(const uint8_t *bits, int64_t n_bits, int32_t stats[3], int nmea_fd)
+{
+	struct demod_state_t d;
+	struct serial_state_t ser;
+	char chunk[4096];
+	memset(&ser, 0, sizeof(ser));
+	ser.fd = nmea_fd;
+	protodec_initialize(&d, nmea_fd >= 0 ? &ser : NULL, NULL, 'A');
+	for (int64_t off = 0; off < n_bits; off += (int64_t) sizeof(chunk)) {
+		int n = (int) ((n_bits - off < (int64_t) sizeof(chunk)) ? n_bits - off : (int64_t) sizeof(chunk));
+		for (int i = 0; i < n; i++)
+			chunk[i] = (char) (bits[off + i] & 1);
+		protodec_decode(chunk, n, &d);
+	}
+	stats[0] = (int32_t) d.receivedframes;
+	stats[1] = (int32_t) d.lostframes;
+	stats[2] = (int32_t) d.lostframes2;
+	protodec_deinit(&d);
+	return 0;
+}
+
+/*
  * Run one reference receiver over frame-interleaved int16 audio exactly as main() does
  * (src/ais.c:214-248): receiver_run() per `chunk` frames.
  *

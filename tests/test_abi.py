@@ -103,3 +103,19 @@ def test_host_synth_is_deterministic_and_layout_consistent():
     c = synth_host(p, 1, 3000, first_channel=2)
     assert np.array_equal(c[0], a[2, :3000])
     assert a.std() > 1000 and abs(int(a.max())) < 20000
+
+
+def test_host_alloc_fails_cleanly_without_a_gpu():
+    """gais_host_alloc() is page-locked memory from the CUDA runtime: on a box without a device it must
+    return an error code (and a NULL pointer), never crash; gais_host_free(NULL) is a no-op"""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is visible: the allocation succeeds (covered by the -m gpu tests)")
+    lib = L.load()
+    p = C.c_void_p(123)
+    assert lib.gais_host_alloc(None, 64) != 0
+    rc = lib.gais_host_alloc(C.byref(p), 1 << 20)
+    assert rc != 0 and not p.value
+    assert b"cudaHostAlloc" in lib.gais_last_error()
+    lib.gais_host_free(None)

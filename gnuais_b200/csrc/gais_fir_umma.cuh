@@ -55,7 +55,7 @@ constexpr int U_BUF_BYTES = U_CH * U_ROW_BYTES;        /* 9472 */
 constexpr int U_BUF_STRIDE = (U_BUF_BYTES + 511) / 512 * 512;   /* 9728: a multiple of the swizzle period, so that
                                                           swz64(a + buf * stride) = swz64(a) + buf * stride */
 constexpr int U_THREADS = 128;
-constexpr int U_LD = (U_CH * U_ROW_CHUNKS + U_THREADS - 1) / U_THREADS;   /* 16-byte loads per thread per stage: 5 */
+constexpr int U_LD = 2 * ((U_ROW_CHUNKS + 7) / 8);      /* 16-byte loads per thread per stage it moves: 64 threads, 2 rows x 5 chunks each */
 constexpr int U_BK_BYTES = 96 * 32;                    /* one k-step of B: 96 rows x 32 bytes */
 constexpr int U_BMAT_BYTES = 3 * U_BK_BYTES;           /* 9216 */
 constexpr int U_SMEM_BYTES = U_BMAT_BYTES + 2 * U_BUF_STRIDE + 1024;   /* + alignment slack */
@@ -65,6 +65,7 @@ constexpr int U_TMEM_COLS = 128;
 #define U_STAGES_PER_BLOCK 48
 #endif
 constexpr int U_TAP_LO = 12, U_TAP_HI = 23;            /* taps with T_i != 0 */
+constexpr int U_VGUARD = 8192;                         /* 0.125 in units of 2^-16: above the 0.103 error bound of the header */
 
 /* instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A = s8, B = u8, both K-major, N = 96, M = 128 */
 constexpr uint32_t U_IDESC = (2u << 4) | (1u << 7) | (0u << 10) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
@@ -169,20 +170,12 @@ __device__ __noinline__ uint32_t umma_sign_resolve(uint32_t w36)
 	return s > 0.0f ? 1u : 0u;
 }
 
-/* settle the outputs marked in pend (bit j = output j of this lane's word); returns the word with those bits corrected */
-__device__ __noinline__ uint32_t umma_resolve_pending(uint32_t word, uint32_t pend, uint32_t w36_0)
-{
-	while (pend) {
-		const uint32_t j = (uint32_t) __ffs((int) pend) - 1u;
-		pend &= pend - 1u;
-		word = (word & ~(1u << j)) | (umma_sign_resolve(w36_0 + 2u * j) << j);
-	}
-	return word;
-}
-
-/* 16 outputs from three accumulator slices: sign bits (1 = Q < 0) and the marks of Q == 0 */
+/* 16 outputs from three accumulator slices.  rev collects the sign bits of Q (output 0 ends at bit 15);
+ * the rare Q == 0 outputs are looked at again with the exact V = (p & 0xffff) - 32768: V <= -8192 is a
+ * certain negative (clr), |V| < 8192 stays open (pend), V >= 8192 is a certain positive.  The unrolled
+ * scan is only entered by warps in which some lane saw a zero, one 4-output chain at a time. */
 __device__ __forceinline__ void umma_half_word(const uint32_t (&d24)[16], const uint32_t (&d16)[16], const uint32_t (&d8)[16], int kc,
-					       uint32_t &neg, uint32_t &pend)
+					       uint32_t &neg, uint32_t &clr, uint32_t &pend)
 {
 	int q[16];
 	uint32_t mn[4], rev = 0;
@@ -190,32 +183,112 @@ __device__ __forceinline__ void umma_half_word(const uint32_t (&d24)[16], const 
 	for (int j = 0; j < 16; j++) {
 		const int p = (int) d16[j] * 256 + (int) d8[j] + kc;
 		q[j] = (int) d24[j] + (p >> 16);
-		rev = __funnelshift_l((uint32_t) q[j], rev, 1);      /* sign bits, output 0 ends at bit 15 */
+		rev = __funnelshift_l((uint32_t) q[j], rev, 1);
 	}
 	neg = __brev(rev) >> 16;
 #pragma unroll
 	for (int c = 0; c < 4; c++)
 		mn[c] = min(min((uint32_t) q[4 * c], (uint32_t) q[4 * c + 1]), min((uint32_t) q[4 * c + 2], (uint32_t) q[4 * c + 3]));
 	pend = 0;
+	clr = 0;
 	if (min(min(mn[0], mn[1]), min(mn[2], mn[3])) == 0u) {
 #pragma unroll
 		for (int c = 0; c < 4; c++)
 			if (mn[c] == 0u) {
 #pragma unroll
 				for (int j = 4 * c; j < 4 * c + 4; j++)
-					if (q[j] == 0)
-						pend |= 1u << j;
+					if (q[j] == 0) {
+						const int v = (((int) d16[j] * 256 + (int) d8[j] + kc) & 0xffff) - 32768;
+						if (v <= -U_VGUARD)
+							clr |= 1u << j;
+						else if (v < U_VGUARD)
+							pend |= 1u << j;
+					}
 			}
 	}
 }
 
+/* ---- the open outputs (2.6e-4 of noisy audio) are not settled where they are found -- one lane of a warp
+ * walking tiers 2/3 costs the whole warp ~200 issue slots -- but queued per CTA and settled 32+ at a time,
+ * one per lane, from global memory; the sign word already written carries a provisional 1 that is cleared
+ * with an atomic when the exact answer is "not > 0". ---- */
+constexpr int U_QCAP = 128, U_QDRAIN = 64;
+
+/* sample t of a channel row of the tile (t < 0: the carried history, src/filter.c:129-134) as float */
+__device__ __forceinline__ float umma_sample(const int16_t *__restrict__ row, const int16_t *__restrict__ hist, int t)
+{
+	return (float) (t >= 0 ? row[t] : (t >= -GAIS_NTAPS ? hist[GAIS_NTAPS + t] : (int16_t) 0));
+}
+
+/* tiers 2 and 3 of gais_fir.cuh for output n of a channel, read from global memory */
+__device__ __noinline__ uint32_t umma_resolve_global(const int16_t *__restrict__ row, const int16_t *__restrict__ hist, int n)
+{
+	float xs[GAIS_NTAPS];
+#pragma unroll
+	for (int i = 2; i < GAIS_NTAPS - 2; i++)
+		xs[i] = umma_sample(row, hist, n - GAIS_NTAPS + i);
+	float a = 0.0f, sabs = 0.0f;
+#pragma unroll
+	for (int i = 12; i <= 23; i++) {
+		a = fmaf(xs[i], c_taps[i], a);
+		sabs = fmaf(fabsf(xs[i]), c_taps[i], sabs);
+	}
+	if (fabsf(a) > fmaf(F_E2_SLOPE, sabs, F_E2_BASE))
+		return a > 0.0f ? 1u : 0u;
+	float s = 0.0f;            /* tier 3: the reference's own arithmetic (src/filter.h:40-49) */
+#pragma unroll
+	for (int i = 2; i < GAIS_NTAPS - 2; i++)
+		s = __fadd_rn(s, __fmul_rn(xs[i], c_taps[i]));
+	return s > 0.0f ? 1u : 0u;
+}
+
+/* queue the open outputs of one sign word; when the queue is full they are settled on the spot from the
+ * shared-memory row.  Returns the bits to clear in that case (bits 0..15), bit 16 = something was queued,
+ * bit 17 = the queue has reached the length at which the CTA settles it */
+__device__ __noinline__ uint32_t umma_push(uint32_t pend, uint32_t item0, uint32_t qn_a, uint32_t q_a, uint32_t w36_0)
+{
+	uint32_t clr = 0;
+	while (pend) {
+		const uint32_t j = (uint32_t) __ffs((int) pend) - 1u;
+		pend &= pend - 1u;
+		uint32_t pos;
+		asm volatile("atom.shared::cta.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(qn_a) : "memory");
+		if (pos < (uint32_t) U_QCAP) {
+			asm volatile("st.shared.u32 [%0], %1;" ::"r"(q_a + 4u * pos), "r"(item0 + j) : "memory");
+			clr |= 1u << 16;
+		} else if (umma_sign_resolve(w36_0 + 2u * j) == 0u)
+			clr |= 1u << j;
+		if (pos + 1u >= (uint32_t) U_QDRAIN)
+			clr |= 1u << 17;
+	}
+	return clr;
+}
+
+struct UmmaRegs { uint4 v[U_LD]; };      /* the 16-byte chunks of a stage a thread moves (see the loader in the kernel) */
+
+/* first stage of a tile: the 40 samples before the tile come from the carried history (4 zeros + 36 samples,
+ * src/filter.c:57-71 / :129-134) -- chunks 0..4 of each row, i.e. k == 0 of the threads with tid % 8 < 5 */
+__device__ __noinline__ uint4 umma_hist_chunk(const ChanState *__restrict__ st_row, int hist_sel, int ch)
+{
+	uint32_t w[4];
+#pragma unroll
+	for (int e = 0; e < 4; e++) {
+		const int t0 = 8 * ch + 2 * e - (U_HALO - GAIS_NTAPS);      /* index into hist[] */
+		const uint32_t lo = t0 >= 0 ? (uint16_t) st_row->hist[hist_sel][t0] : 0u;
+		const uint32_t hi = t0 + 1 >= 0 ? (uint16_t) st_row->hist[hist_sel][t0 + 1] : 0u;
+		w[e] = lo | (hi << 16);
+	}
+	return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 __global__ void __launch_bounds__(U_THREADS, 4)
 fir_sign_umma_kernel(const int16_t *__restrict__ base, int64_t ch_stride, ChanState *__restrict__ st, int hist_sel, int n_channels,
-		     int n_stages, int stages_per_block, uint32_t *__restrict__ signs, int save_hist, int kc)
+		     int n_stages, int stages_per_block, uint32_t *__restrict__ signs, int save_hist, int kc, int dbg)
 {
 	extern __shared__ __align__(1024) uint8_t u_smem_raw[];
 	__shared__ __align__(8) uint64_t mma_bar;
 	__shared__ uint32_t tmem_base_s;
+	__shared__ uint32_t q_n, q_item[U_QCAP];      /* open outputs: (channel of the group << 28) | sample index in the tile */
 
 	const int tid = threadIdx.x, warp = tid >> 5;
 	const int cg = blockIdx.x * U_CH;
@@ -233,62 +306,56 @@ fir_sign_umma_kernel(const int16_t *__restrict__ base, int64_t ch_stride, ChanSt
 	if (tid == 0) {
 		mbar_init(bar_a, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		q_n = 0;
 	}
 	if (warp == 0) {
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(U_TMEM_COLS) : "memory");
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 	}
 
-	/* ---- loader: thread t owns 16-byte chunks t, t + 128, ... of the 16 x 37 chunk stage ---- */
-	const int16_t *gsrc[U_LD];
-	uint32_t sdst[U_LD];
+	/* ---- loader.  A thread's global loads share one scoreboard, so loads issued for a later stage would
+	 * hold up the use of an earlier one; instead the two warp pairs alternate: pair p moves the stages of
+	 * parity p, issues the loads of stage k + 2 right after it has stored stage k, and uses them a full
+	 * stage later.  64 threads x 10 chunks: rows (tid/8) and (tid/8)+8, chunks (tid%8) + 8 j, j = 0..4 ---- */
+	const int lpar = warp >> 1, lt = tid & 63;
+	const int lrow = lt >> 3, lsub = lt & 7;
+	const bool last_valid = lsub < U_ROW_CHUNKS - 8 * (U_LD / 2 - 1);
+	/* chunk lsub of row lrow of stage s_begin; stage it is 32 chunks (512 B) further, row lrow + 8 is gp8 */
+	const uint4 *gp = reinterpret_cast<const uint4 *>(base + (int64_t) (cg + lrow) * ch_stride + (int64_t) s_begin * U_T - U_HALO) + lsub;
+	const int64_t gp8 = ch_stride;                /* 8 rows further, in uint4 units (8 * ch_stride * 2 / 16) */
+	uint32_t sdst[U_LD / 2];
 #pragma unroll
-	for (int k = 0; k < U_LD; k++) {
-		const int qi = tid + U_THREADS * k;
-		const int row = qi / U_ROW_CHUNKS, ch = qi % U_ROW_CHUNKS;
-		gsrc[k] = base + (int64_t) (cg + row) * ch_stride + (int64_t) s_begin * U_T - U_HALO + 8 * ch;
-		sdst[k] = swz64(buf_a + row * U_ROW_BYTES + ch * 16);
-	}
-	constexpr bool tail_chunk = (U_CH * U_ROW_CHUNKS) % U_THREADS != 0;
-	const bool last_valid = !tail_chunk || tid + U_THREADS * (U_LD - 1) < U_CH * U_ROW_CHUNKS;
-	uint4 pre[U_LD];
+	for (int j = 0; j < U_LD / 2; j++)
+		sdst[j] = swz64(buf_a + lrow * U_ROW_BYTES + (lsub + 8 * j) * 16);
+	/* rows lrow + 8 sit 8 * 592 = 4736 B further: 4736 = 9 * 512 + 128, so their swizzle phase differs */
+	uint32_t sdst8[U_LD / 2];
+#pragma unroll
+	for (int j = 0; j < U_LD / 2; j++)
+		sdst8[j] = swz64(buf_a + (lrow + 8) * U_ROW_BYTES + (lsub + 8 * j) * 16);
 
+	UmmaRegs pre;
 	auto load_stage = [&](int it) {
-		const int s = s_begin + it;
+		const uint4 *g = gp + (int64_t) it * (U_T / 8);
+		if (dbg & 1)          /* GAIS_FIR_DBG=1 (diagnostics only): no global loads after the first stages */
+			return;
 #pragma unroll
-		for (int k = 0; k < U_LD; k++) {
-			if (k == U_LD - 1 && !last_valid)
-				continue;
-			if (s == 0) {
-				/* first stage of the tile: samples before the tile come from the carried history
-				 * (4 zeros + 36 samples, src/filter.c:57-71 / :129-134) */
-				const int qi = tid + U_THREADS * k;
-				const int row = qi / U_ROW_CHUNKS, ch = qi % U_ROW_CHUNKS;
-				if (ch < U_HALO / 8) {
-					uint32_t w[4];
-#pragma unroll
-					for (int e = 0; e < 4; e++) {
-						const int t0 = 8 * ch + 2 * e - (U_HALO - GAIS_NTAPS);      /* index into hist[] */
-						const uint32_t lo = t0 >= 0 ? (uint16_t) st[cg + row].hist[hist_sel][t0] : 0u;
-						const uint32_t hi = t0 + 1 >= 0 ? (uint16_t) st[cg + row].hist[hist_sel][t0 + 1] : 0u;
-						w[e] = lo | (hi << 16);
-					}
-					pre[k] = make_uint4(w[0], w[1], w[2], w[3]);
-					continue;
-				}
+		for (int j = 0; j < U_LD / 2; j++)
+			if (j < U_LD / 2 - 1 || last_valid) {
+				pre.v[2 * j] = __ldg(g + 8 * j);
+				pre.v[2 * j + 1] = __ldg(g + gp8 + 8 * j);
 			}
-			pre[k] = __ldg(reinterpret_cast<const uint4 *>(gsrc[k] + (int64_t) it * U_T));
-		}
 	};
 	auto store_stage = [&](int buf) {
 #pragma unroll
-		for (int k = 0; k < U_LD; k++) {
-			if (k == U_LD - 1 && !last_valid)
-				continue;
-			asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sdst[k] + buf * U_BUF_STRIDE), "r"(pre[k].x ^ 0x00800080u),
-				     "r"(pre[k].y ^ 0x00800080u), "r"(pre[k].z ^ 0x00800080u), "r"(pre[k].w ^ 0x00800080u)
-				     : "memory");
-		}
+		for (int j = 0; j < U_LD / 2; j++)
+			if (j < U_LD / 2 - 1 || last_valid) {
+				asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sdst[j] + buf * U_BUF_STRIDE), "r"(pre.v[2 * j].x ^ 0x00800080u),
+					     "r"(pre.v[2 * j].y ^ 0x00800080u), "r"(pre.v[2 * j].z ^ 0x00800080u), "r"(pre.v[2 * j].w ^ 0x00800080u)
+					     : "memory");
+				asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sdst8[j] + buf * U_BUF_STRIDE), "r"(pre.v[2 * j + 1].x ^ 0x00800080u),
+					     "r"(pre.v[2 * j + 1].y ^ 0x00800080u), "r"(pre.v[2 * j + 1].z ^ 0x00800080u), "r"(pre.v[2 * j + 1].w ^ 0x00800080u)
+					     : "memory");
+			}
 		/* the tensor core reads shared memory through the async proxy */
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	};
@@ -307,14 +374,32 @@ fir_sign_umma_kernel(const int16_t *__restrict__ base, int64_t ch_stride, ChanSt
 		asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_a) : "memory");
 	};
 
-	load_stage(0);
+	if (lpar == 0) {
+		if (s_begin == 0) {
+			/* the chunks before the tile start must not be read from global memory */
+#pragma unroll
+			for (int j = 0; j < U_LD / 2; j++)
+				if (j < U_LD / 2 - 1 || last_valid) {
+					if (j == 0 && lsub < U_HALO / 8) {
+						pre.v[0] = umma_hist_chunk(st + cg + lrow, hist_sel, lsub);
+						pre.v[1] = umma_hist_chunk(st + cg + lrow + 8, hist_sel, lsub);
+					} else {
+						pre.v[2 * j] = __ldg(gp + 8 * j);
+						pre.v[2 * j + 1] = __ldg(gp + gp8 + 8 * j);
+					}
+				}
+		} else
+			load_stage(0);
+	} else if (n_it > 1)
+		load_stage(1);
 	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 	__syncthreads();                              /* B matrix, barrier init and the TMEM address are visible */
 	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 	const uint32_t tmem = tmem_base_s;
-	store_stage(0);
+	if (lpar == 0)
+		store_stage(0);
 	__syncthreads();
-	if (tid == 0) {
+	if (tid == 0 && !(dbg & 4)) {
 		asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 		issue_mma(0, tmem);
 	}
@@ -327,38 +412,60 @@ fir_sign_umma_kernel(const int16_t *__restrict__ base, int64_t ch_stride, ChanSt
 	/* linear shared address of x[n-36] for output 0 of this row: the row starts at sample t0 - 40, output j of
 	 * word r is sample t0 + 32 r + j */
 	const uint32_t w36 = buf_a + c * U_ROW_BYTES + (32 * r + U_HALO - GAIS_NTAPS) * 2;
+	uint32_t qflags = 0;          /* bit 0: this thread has queued something since the last settling; bit 1: queue long enough */
 
 	for (int it = 0; it < n_it; it++) {
 		const int buf = it & 1;
-		if (it + 1 < n_it)
-			load_stage(it + 1);           /* global loads of the next stage fly while this one is finished */
-		mbar_wait(bar_a, (uint32_t) (it & 1));
+		if ((it & 1) == lpar && it + 2 < n_it)
+			load_stage(it + 2);           /* this pair stored stage `it` a stage ago: its registers are free */
+		if (!(dbg & 4))       /* GAIS_FIR_DBG=4 (diagnostics only): no tensor-core work */
+			mbar_wait(bar_a, (uint32_t) (it & 1));
 		asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
 		uint32_t word = 0;
+		if (!(dbg & 2))       /* GAIS_FIR_DBG=2 (diagnostics only): no epilogue */
 #pragma unroll
 		for (int h = 0; h < 2; h++) {
-			uint32_t d24[16], d16[16], d8[16], neg, pend;
+			uint32_t d24[16], d16[16], d8[16], neg, clr, pend;
 			tmem_ld16(taddr + 16 * h, d24);
 			tmem_ld16(taddr + 32 + 16 * h, d16);
 			tmem_ld16(taddr + 64 + 16 * h, d8);
 			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-			umma_half_word(d24, d16, d8, kc, neg, pend);
-			uint32_t w = ~neg & 0xffffu;          /* bit j = (Q >= 0); the Q == 0 ones are settled below */
-			if (pend)
-				w = umma_resolve_pending(w, pend, w36 + buf * U_BUF_STRIDE + 32 * h);
-			word |= w << (16 * h);
+			umma_half_word(d24, d16, d8, kc, neg, clr, pend);
+			if (pend) {    /* queued with a provisional 1; settled below, 32+ at a time */
+				clr |= umma_push(pend, ((uint32_t) c << 28) | (uint32_t) ((s_begin + it) * U_T + 32 * r + 16 * h), smem_u32(&q_n),
+						 smem_u32(q_item), w36 + buf * U_BUF_STRIDE + 32 * h);
+				qflags |= clr >> 16;
+			}
+			word |= (~(neg | clr) & 0xffffu) << (16 * h);      /* bit j = (filtered[32 w + j] > 0) */
 		}
 		*sp = word;
 		sp += sp_step;
 
 		asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-		if (it + 1 < n_it)
+		if (((it + 1) & 1) == lpar && it + 1 < n_it)
 			store_stage(buf ^ 1);
-		__syncthreads();                      /* TMEM drained by every warp, next stage complete in shared memory */
-		if (it + 1 < n_it && tid == 0) {
+		/* the barrier: TMEM drained by every warp, next stage complete in shared memory; it also carries the
+		 * decision to settle the queue (long enough, or the CTA's last stage with something in it), so that
+		 * every thread takes the same branch */
+		const int settle = __syncthreads_or((int) ((qflags & 2u) | (it + 1 == n_it ? (qflags & 1u) : 0u)));
+		if (it + 1 < n_it && tid == 0 && !(dbg & 4)) {
 			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 			issue_mma(buf ^ 1, tmem);
+		}
+		if (settle) {
+			const uint32_t nq = min(q_n, (uint32_t) U_QCAP);
+			qflags = 0;
+			if ((uint32_t) tid < nq) {
+				const uint32_t item = q_item[tid];
+				const int qc = (int) (item >> 28), n = (int) (item & 0x0fffffffu);
+				if (umma_resolve_global(base + (int64_t) (cg + qc) * ch_stride, st[cg + qc].hist[hist_sel], n) == 0u)
+					atomicAnd(signs + (int64_t) (n >> 5) * n_channels + cg + qc, ~(1u << (n & 31)));
+			}
+			__syncthreads();
+			if (tid == 0)
+				q_n = 0;
+			__syncthreads();
 		}
 	}
 
@@ -433,7 +540,7 @@ static inline int fir_launch(int fir_mode, int layout, SampleView view, ChanStat
 		if (umma) {
 			dim3 grid((unsigned) (fast_ch / U_CH), (unsigned) ((n_stages + spb - 1) / spb));
 			fir_sign_umma_kernel<<<grid, U_THREADS, U_SMEM_REQUEST, stream>>>(view.base, view.ch_stride, st, hist_sel, n_ch, n_stages, spb,
-											    signs, fast_frames == n_frames ? 1 : 0, g_umma_kc);
+											    signs, fast_frames == n_frames ? 1 : 0, g_umma_kc, dbg);
 		} else {
 			dim3 grid((unsigned) (fast_ch / F_CH), (unsigned) ((n_stages + spb - 1) / spb));
 			CUtensorMap tm;

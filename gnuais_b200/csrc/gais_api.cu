@@ -20,6 +20,7 @@
 #include "gais_kernels.cuh"
 #include "gais_fir.cuh"
 #include "gais_fir_umma.cuh"
+#include "gais_fir_tc.cuh"
 #include "gais_track.cuh"
 
 using namespace gais;
@@ -282,7 +283,7 @@ extern "C" int gais_create(const gais_config *cfg, gais_ctx **out)
 	}
 	if ((rc = upload_taps()) != 0)
 		goto bad;
-	if ((rc = fir_setup()) != 0 || (rc = fir_umma_setup()) != 0) {
+	if ((rc = fir_setup()) != 0 || (rc = fir_umma_setup()) != 0 || (rc = fir_tc_setup(cfg->device)) != 0) {
 		rc = fail(GAIS_ECUDA, "fir_setup failed: %s", cudaGetErrorString(cudaGetLastError()));
 		goto bad;
 	}

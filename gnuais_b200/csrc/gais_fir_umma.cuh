@@ -496,89 +496,5 @@ static inline int fir_umma_setup(void)
 }
 
 
-/* which fast kernel GAIS_FIR_GUARD uses: 1 = tensor-pipe integer FIR (this file, default), 0 = FFMA2 guard band
- * (gais_fir.cuh; GAIS_FIR_IMPL=ffma2 keeps it selectable for A/B runs and as the second witness in the tests) */
-static inline int fir_impl_umma(void)
-{
-	static int v = -1;
-	if (v < 0) {
-		const char *e = getenv("GAIS_FIR_IMPL");
-		v = (e && strcmp(e, "ffma2") == 0) ? 0 : 1;
-	}
-	return v;
-}
-
-/*
- * Launch K1 for one time tile.  The fast kernel takes the part of the tile it is built for
- * (planar rows, 16-byte aligned, whole channel groups, whole 256-sample stages); the exact
- * kernel sweeps up the ragged remainder (and everything in GAIS_FIR_EXACT mode).
- * Returns the number of kernels launched, < 0 on error.
- */
-static inline int fir_launch(int fir_mode, int layout, SampleView view, ChanState *st, int hist_sel, int n_ch,
-			     int64_t n_frames, uint32_t *signs, cudaStream_t stream, int *hist_saved_channels)
-{
-	int launches = 0;
-	int fast_ch = 0;
-	*hist_saved_channels = 0;
-	int64_t fast_frames = 0;
-	const bool aligned = layout == GAIS_LAYOUT_PLANAR && view.t_stride == 1 && (view.ch_stride % 8) == 0 &&
-			     ((uintptr_t) view.base % 16) == 0;
-	const bool umma = fir_impl_umma() != 0;
-	if (fir_mode == GAIS_FIR_GUARD && aligned) {
-		fast_ch = umma ? n_ch / U_CH * U_CH : n_ch / F_CH * F_CH;
-		fast_frames = n_frames / F_T * F_T;
-	}
-	if (fast_ch > 0 && fast_frames > 0) {
-		const int n_stages = (int) (fast_frames / F_T);
-		static int spb = 0, dbg = 0;
-		if (!spb) {
-			const char *e = getenv("GAIS_FIR_SPB");
-			spb = (e && atoi(e) > 0) ? atoi(e) : (umma ? U_STAGES_PER_BLOCK : F_STAGES_PER_BLOCK);
-			e = getenv("GAIS_FIR_DBG");
-			dbg = e ? atoi(e) : 0;
-		}
-		if (umma) {
-			dim3 grid((unsigned) (fast_ch / U_CH), (unsigned) ((n_stages + spb - 1) / spb));
-			fir_sign_umma_kernel<<<grid, U_THREADS, U_SMEM_REQUEST, stream>>>(view.base, view.ch_stride, st, hist_sel, n_ch, n_stages, spb,
-											    signs, fast_frames == n_frames ? 1 : 0, g_umma_kc, dbg);
-		} else {
-			dim3 grid((unsigned) (fast_ch / F_CH), (unsigned) ((n_stages + spb - 1) / spb));
-			CUtensorMap tm;
-			if (!fir_make_tmap(&tm, view.base, view.ch_stride, fast_ch, fast_frames))
-				return -1;
-#define F_LAUNCH(D) fir_sign_fast_kernel<D><<<grid, F_THREADS, F_NSTAGE * F_STAGE_BYTES, stream>>>(tm, view.base, view.ch_stride, st, \
-		hist_sel, n_ch, n_stages, spb, signs, fast_frames == n_frames ? 1 : 0)
-			switch (dbg) {          /* 0 is the product; the others are the diagnostics of profiles/r1_experiments.txt */
-			case 2: F_LAUNCH(2); break;
-			case 4: F_LAUNCH(4); break;
-			case 6: F_LAUNCH(6); break;
-			case 8: F_LAUNCH(8); break;
-			case 16: F_LAUNCH(16); break;
-			case 20: F_LAUNCH(20); break;
-			default: F_LAUNCH(0); break;
-			}
-#undef F_LAUNCH
-		}
-		*hist_saved_channels = (fast_frames == n_frames) ? fast_ch : 0;
-		launches++;
-	} else {
-		fast_ch = 0;
-		fast_frames = 0;
-	}
-	/* remainder in time for the fast channels: frames [fast_frames, n_frames) */
-	if (fast_ch > 0 && fast_frames < n_frames) {
-		dim3 grid((unsigned) ((fast_ch + K1_CH - 1) / K1_CH), (unsigned) ((n_frames - fast_frames + K1_TILE - 1) / K1_TILE));
-		fir_sign_exact_kernel<<<grid, K1_CH * 32, 0, stream>>>(view, st, hist_sel, 0, fast_ch, fast_frames, n_frames, n_ch, signs);
-		launches++;
-	}
-	/* remaining channels, all frames */
-	if (fast_ch < n_ch) {
-		dim3 grid((unsigned) ((n_ch - fast_ch + K1_CH - 1) / K1_CH), (unsigned) ((n_frames + K1_TILE - 1) / K1_TILE));
-		fir_sign_exact_kernel<<<grid, K1_CH * 32, 0, stream>>>(view, st, hist_sel, fast_ch, n_ch, 0, n_frames, n_ch, signs);
-		launches++;
-	}
-	return cudaGetLastError() == cudaSuccess ? launches : -1;
-}
-
 } /* namespace gais */
 #endif

@@ -8,7 +8,7 @@
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
 constexpr int IMG = 96 * 1024;
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
-struct Args { uint64_t a_desc, b_desc; uint32_t a_start, b_start, a_kstep, b_kstep, idesc; int n_mma, ksteps, cols; };
+struct Args { uint64_t a_desc, b_desc; uint32_t a_start, b_start, a_kstep, b_kstep, idesc; int n_mma, ksteps, cols; int alt; uint32_t idesc2; };
 
 __global__ void __launch_bounds__(128, 1) rate_kernel(Args pa, long long *out)
 {
@@ -46,11 +46,17 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(Args pa, long long *out)
 		uint32_t slot = 0;
 		for (int i = 0; i < pa.n_mma; i += 4) {
 #pragma unroll
-			for (int k = 0; k < 4; k++)
+			for (int k = 0; k < 4; k++) {
+				/* alt 0: same MMA every time.  alt 1: odd MMAs use the second instruction descriptor (A = u8, N = 64) on
+				 * columns +32 of the same slot.  alt 2: second descriptor, same columns.  alt 3: same descriptor, columns +32. */
+				const bool second = pa.alt && (k & 1);
+				const uint32_t id = (second && pa.alt != 3) ? pa.idesc2 : pa.idesc;
+				const uint32_t dd = tmem + slot + ((second && pa.alt != 2) ? 32u : 0u);
 				asm volatile(
 					"{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
 					"tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-					::"r"(tmem + slot), "l"(ad[k]), "l"(bd[k]), "r"(pa.idesc), "r"(k ? 1u : 0u), "r"(0u) : "memory");
+					::"r"(dd), "l"(ad[k]), "l"(bd[k]), "r"(id), "r"(k ? 1u : 0u), "r"(0u) : "memory");
+			}
 			slot = (slot + pa.cols) & 511u;
 		}
 		long long t1 = clock64();
@@ -71,7 +77,7 @@ static uint64_t make_desc(uint32_t lbo, uint32_t sbo, uint32_t layout)
 	return ((uint64_t) ((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t) ((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t) 1 << 46) | ((uint64_t) (layout & 7) << 61);
 }
 static uint32_t idesc_i8(int M, int N) { return (2u << 4) | (1u << 7) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24); }
-struct Cfg { const char *name; uint32_t a_lbo, a_sbo, a_layout, a_start, a_kstep; int N, ksteps; uint32_t b_lbo, b_sbo, b_layout, b_kstep; };
+struct Cfg { const char *name; uint32_t a_lbo, a_sbo, a_layout, a_start, a_kstep; int N, ksteps; uint32_t b_lbo, b_sbo, b_layout, b_kstep; int alt; };
 int main()
 {
 	CK(cudaSetDevice(0));
@@ -89,14 +95,17 @@ int main()
 		{ "A sw128 standard, N32, B sw128 standard", 16, 1024, 2, 0, 32, 32, 4, 16, 1024, 2, 32 },
 		{ "A sw64 overlapped sbo592, N32, 3 ksteps, B none", 16, 592, 4, 32, 32, 32, 3, 128, 256, 0, 1024 },
 		{ "A sw64 overlapped sbo592, N96, B sw128 standard", 16, 592, 4, 32, 32, 96, 3, 16, 1024, 2, 32 },
+		{ "FIR tc: alternate (s8,N96,d) / (u8,N64,d+32)", 16, 576, 4, 16, 32, 96, 4, 128, 256, 0, 3072, 1 },
+		{ "alternate (s8,N96,d) / (u8,N64,d)", 16, 576, 4, 16, 32, 96, 4, 128, 256, 0, 3072, 2 },
+		{ "alternate (s8,N96,d) / (s8,N96,d+32)", 16, 576, 4, 16, 32, 96, 4, 128, 256, 0, 3072, 3 },
 	};
-	for (int grid : { 1, 148 })
+	for (int grid : { 1 })
 		for (const Cfg &c : cfgs) {
 			Args a;
 			a.a_desc = make_desc(c.a_lbo, c.a_sbo, c.a_layout);
 			a.b_desc = make_desc(c.b_lbo, c.b_sbo, c.b_layout);
 			a.a_start = c.a_start; a.b_start = 64 * 1024; a.a_kstep = c.a_kstep; a.b_kstep = c.b_kstep;
-			a.idesc = idesc_i8(128, c.N); a.ksteps = c.ksteps; a.cols = c.N <= 128 ? 128 : 256;
+			a.idesc = idesc_i8(128, c.N); a.alt = c.alt; a.idesc2 = (2u << 4) | ((uint32_t) (64 >> 3) << 17) | ((uint32_t) (128 >> 4) << 24); a.ksteps = c.ksteps; a.cols = c.N <= 128 ? 128 : 256;
 			a.n_mma = 1200;
 			rate_kernel<<<grid, 128, IMG + 1024>>>(a, d_out);
 			CK(cudaDeviceSynchronize());

@@ -16,7 +16,7 @@ LIB_PATH = _HERE / "lib" / "libgaisb200.so"
 ABI_VERSION = 1
 LAYOUT_PLANAR, LAYOUT_INTERLEAVED = 0, 1
 FIR_GUARD, FIR_EXACT = 0, 1
-KEEP_BITS, KEEP_SIGNS = 1, 2
+KEEP_BITS, KEEP_SIGNS, KEEP_PEAK = 1, 2, 4
 NMEA_STRIDE = 176
 E_OVERFLOW = -5
 
@@ -95,9 +95,13 @@ SYMBOLS = {
     "gais_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
     "gais_destroy": (None, [_P]),
     "gais_reset": (C.c_int, [_P]),
+    "gais_reset_fsm": (C.c_int, [_P]),
     "gais_run_device": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
     "gais_run_host": (C.c_int, [_P, _P, C.c_int64, C.c_int64]),
     "gais_sync": (C.c_int, [_P]),
+    "gais_run_bits_device": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
+    "gais_run_bits_host": (C.c_int, [_P, _P, C.c_int64, C.c_int64]),
+    "gais_get_peaks": (C.c_int, [_P, _P]),
     "gais_message_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "gais_get_messages": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "gais_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),

@@ -77,6 +77,7 @@ struct gais_ctx {
 	int64_t nmea_cap;
 	uint32_t *d_bits;
 	int bits_row_words;
+	int16_t *d_peak;            /* GAIS_KEEP_PEAK */
 	int32_t *d_overflow;
 	unsigned long long *d_totals;
 	int16_t *d_stage[2];        /* gais_run_host staging tiles */
@@ -140,6 +141,30 @@ extern "C" int gais_reset(gais_ctx *ctx)
 	return 0;
 }
 
+__global__ void reset_fsm_kernel(ChanState *st, int n)
+{
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c < n) {
+		st[c].fsm = (uint8_t) hdlc_hunt_id(0, 0, 0);      /* src/protodec.c:87-100 */
+		st[c].pos = 0;
+	}
+}
+
+static int finish(gais_ctx *ctx);
+
+extern "C" int gais_reset_fsm(gais_ctx *ctx)
+{
+	if (!ctx)
+		return fail(GAIS_EINVAL, "null ctx");
+	int rc = finish(ctx);
+	if (rc && rc != GAIS_EOVERFLOW)
+		return rc;
+	reset_fsm_kernel<<<(ctx->n_ch + 127) / 128, 128>>>(ctx->d_state, ctx->n_ch);
+	CK(cudaGetLastError());
+	CK(cudaDeviceSynchronize());
+	return 0;
+}
+
 extern "C" void gais_destroy(gais_ctx *ctx)
 {
 	if (!ctx)
@@ -156,6 +181,7 @@ extern "C" void gais_destroy(gais_ctx *ctx)
 	cudaFree(ctx->d_dense);
 	cudaFree(ctx->d_nmea);
 	cudaFree(ctx->d_bits);
+	cudaFree(ctx->d_peak);
 	cudaFree(ctx->d_overflow);
 	cudaFree(ctx->d_totals);
 	cudaFree(ctx->d_stage[0]);
@@ -259,6 +285,8 @@ extern "C" int gais_create(const gais_config *cfg, gais_ctx **out)
 			ctx->bits_row_words = (int) ((max_bits + 31) / 32);
 			CKC(cudaMalloc(&ctx->d_bits, (size_t) ctx->n_ch * ctx->bits_row_words * 4));
 		}
+		if (cfg->flags & GAIS_KEEP_PEAK)
+			CKC(cudaMalloc(&ctx->d_peak, (size_t) ctx->n_ch * 2));
 		CKC(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
 		CKC(cudaStreamCreateWithFlags(&ctx->s_own, cudaStreamNonBlocking));
 		{
@@ -368,6 +396,10 @@ static int enqueue_tile(gais_ctx *ctx, SampleView view, int64_t n_frames, int ti
 		ctx->launches++;
 	}
 	ctx->hist_sel ^= 1;
+	if (ctx->d_peak) {
+		peak_kernel<<<(unsigned) (((int64_t) ctx->n_ch * 32 + 255) / 256), 256, 0, st>>>(view, ctx->n_ch, n_frames, ctx->d_peak);
+		ctx->launches++;
+	}
 	if (timed) CK(cudaEventRecord(ctx->ev_tile[4 * tile_idx + 1], st));
 	if (overlap) {
 		CK(cudaEventRecord(ctx->ev_fir_done[tile_idx & 1], st));
@@ -400,6 +432,8 @@ static int begin_run(gais_ctx *ctx, int64_t n_frames, cudaStream_t st)
 	CK(cudaMemsetAsync(ctx->d_run_bits, 0, sizeof(uint32_t) * ctx->n_ch, st));
 	if (ctx->d_bits)
 		CK(cudaMemsetAsync(ctx->d_bits, 0, (size_t) ctx->n_ch * ctx->bits_row_words * 4, st));
+	if (ctx->d_peak)
+		CK(cudaMemsetAsync(ctx->d_peak, 0, (size_t) ctx->n_ch * 2, st));
 	return 0;
 }
 
@@ -512,6 +546,66 @@ extern "C" int gais_run_host(gais_ctx *ctx, const int16_t *h_samples, int64_t n_
 	ctx->pending = 1;
 	ctx->n_tiles_last = n_tiles;
 	return 0;
+}
+
+extern "C" int gais_run_bits_device(gais_ctx *ctx, const uint8_t *d_bits, int64_t n_bits, int64_t stride, void *stream)
+{
+	if (!ctx || !d_bits)
+		return fail(GAIS_EINVAL, "null argument");
+	if (stride < n_bits)
+		return fail(GAIS_EINVAL, "stride %lld smaller than n_bits", (long long) stride);
+	cudaStream_t st = (cudaStream_t) stream;
+	int rc = begin_run(ctx, n_bits, st);
+	if (rc)
+		return rc;
+	if ((rc = ensure_tile_events(ctx, 1)) != 0)
+		return rc;
+	CK(cudaEventRecord(ctx->ev[EV_START], st));
+	CK(cudaEventRecord(ctx->ev_tile[0], st));
+	CK(cudaEventRecord(ctx->ev_tile[1], st));
+	CK(cudaEventRecord(ctx->ev_tile[2], st));
+	hdlc_bits_kernel<<<(ctx->n_ch + TRK_THREADS - 1) / TRK_THREADS, TRK_THREADS, 0, st>>>(d_bits, stride, n_bits, ctx->d_state, ctx->n_ch,
+												 make_out(ctx));
+	ctx->launches++;
+	CK(cudaEventRecord(ctx->ev_tile[3], st));
+	if ((rc = enqueue_post(ctx, st)) != 0)
+		return rc;
+	CK(cudaEventRecord(ctx->ev[EV_END], st));
+	CK(cudaGetLastError());
+	ctx->last_stream = st;
+	ctx->pending = 1;
+	ctx->n_tiles_last = 1;
+	return 0;
+}
+
+extern "C" int gais_run_bits_host(gais_ctx *ctx, const uint8_t *h_bits, int64_t n_bits, int64_t stride)
+{
+	if (!ctx || !h_bits)
+		return fail(GAIS_EINVAL, "null argument");
+	if (n_bits < 1 || n_bits > ctx->cfg.max_frames_per_run)
+		return fail(GAIS_EINVAL, "n_bits %lld outside 1..max_frames_per_run (%lld)", (long long) n_bits,
+			    (long long) ctx->cfg.max_frames_per_run);
+	if (stride < n_bits)
+		return fail(GAIS_EINVAL, "stride %lld smaller than n_bits", (long long) stride);
+	CK(cudaSetDevice(ctx->cfg.device));
+	/* the sample staging buffers double as the bit staging buffer (they are at least one tile of int16 per channel) */
+	const int64_t need = ((int64_t) ctx->n_ch * n_bits + 1) / 2;
+	if (need > ctx->stage_elems) {
+		CK(cudaStreamSynchronize(ctx->s_copy));
+		CK(cudaStreamSynchronize(ctx->s_own));
+		cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]);
+		ctx->d_stage[0] = ctx->d_stage[1] = NULL;
+		ctx->stage_elems = 0;
+		CK(cudaMalloc(&ctx->d_stage[0], (size_t) need * 2));
+		CK(cudaMalloc(&ctx->d_stage[1], (size_t) need * 2));
+		ctx->stage_elems = need;
+		CK(cudaEventRecord(ctx->ev_free[0], ctx->s_own));
+		CK(cudaEventRecord(ctx->ev_free[1], ctx->s_own));
+	}
+	CK(cudaStreamSynchronize(ctx->s_own));        /* the previous run has read the staging buffer */
+	CK(cudaMemcpy2DAsync(ctx->d_stage[0], (size_t) n_bits, h_bits, (size_t) stride, (size_t) n_bits, (size_t) ctx->n_ch,
+			     cudaMemcpyHostToDevice, ctx->s_own));
+	return gais_run_bits_device(ctx, (const uint8_t *) ctx->d_stage[0], n_bits, n_bits, ctx->s_own);
 }
 
 /* complete the last run: wait, size and fill the dense message array */
@@ -747,6 +841,19 @@ extern "C" int gais_get_signs(gais_ctx *ctx, uint32_t *h_words, int64_t cap_word
 	if (words > cap_words)
 		words = cap_words;
 	CK(cudaMemcpy(h_words, ctx->d_signs[0], (size_t) words * 4, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+extern "C" int gais_get_peaks(gais_ctx *ctx, int16_t *h_out)
+{
+	if (!ctx || !h_out)
+		return fail(GAIS_EINVAL, "null argument");
+	if (!ctx->d_peak)
+		return fail(GAIS_EINVAL, "context was created without GAIS_KEEP_PEAK");
+	int rc = finish(ctx);
+	if (rc && rc != GAIS_EOVERFLOW)
+		return rc;
+	CK(cudaMemcpy(h_out, ctx->d_peak, (size_t) ctx->n_ch * 2, cudaMemcpyDeviceToHost));
 	return 0;
 }
 

@@ -90,11 +90,38 @@ struct TcArgs {
 	int dbg;                   /* GAIS_FIR_DBG, diagnostics only: 2 no epilogue arithmetic, 4 no MMAs, 8 no bit flip */
 };
 
-__global__ void __launch_bounds__(P_THREADS, 4)
+/* named barrier of the four epilogue warps (128 threads) that also ORs a predicate over them */
+__device__ __forceinline__ int epi_sync_or(int pred)
+{
+	int r;
+	asm volatile(
+		"{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %1, 0;\n\t"
+		"barrier.cta.red.or.pred q, 1, 128, p;\n\tselp.b32 %0, 1, 0, q;\n\t}"
+		: "=r"(r) : "r"(pred) : "memory");
+	return r;
+}
+__device__ __forceinline__ void epi_sync(void)
+{
+	asm volatile("barrier.cta.sync 1, 128;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+/*
+ * Roles.  Warps 0-3 (one TMEM lane quadrant each): flip stage k + 1, wait for the accumulators of stage k,
+ * tcgen05.ld -> Q -> sign word -> global, then ARRIVE (not wait) on `ready`.  Warp 4, one lane: waits for the 128
+ * arrivals (= accumulators drained and next stage flipped), issues the three MMAs of the next stage and the TMA
+ * request that refills the buffer the tensor core has just finished with.  Issuing an MMA blocks until the tensor
+ * pipe takes it (~60 cycles each); in a thread that also runs an epilogue that time was on every stage's critical
+ * path, and the CTA-wide barrier it needed cost another fifth of the kernel (profiles/r2_experiments.txt).
+ */
+__global__ void __launch_bounds__(P_THREADS + 32, 4)
 fir_sign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a)
 {
 	extern __shared__ __align__(1024) uint8_t p_smem_raw[];
-	__shared__ __align__(8) uint64_t bars[P_NS + 1];
+	__shared__ __align__(8) uint64_t bars[P_NS + 2];
 	__shared__ uint32_t tmem_base_s;
 	__shared__ uint32_t q_n, q_item[U_QCAP];      /* open outputs: (channel of the group << 28) | sample index in the tile */
 
@@ -104,13 +131,14 @@ fir_sign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a)
 	const int n_it = min(a.stages_per_block, a.n_stages - s_begin);
 	const uint32_t smem0 = (smem_u32(p_smem_raw) + 1023u) & ~1023u;
 	const uint32_t bmat_a = smem0, ring_a = smem0 + U_BMAT_BYTES;
-	const uint32_t full_a = smem_u32(bars), mma_a = full_a + 8 * P_NS;
+	const uint32_t full_a = smem_u32(bars), mma_a = full_a + 8 * P_NS, ready_a = mma_a + 8;
 
 	/* ---- one-time setup: barriers and the first TMA requests, B matrix, TMEM ---- */
-	if (tid == 0) {
+	if (tid == P_THREADS) {
 		for (int i = 0; i < P_NS; i++)
 			mbar_init(full_a + 8 * i, 1);
 		mbar_init(mma_a, 1);
+		mbar_init(ready_a, P_THREADS);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		q_n = 0;
 		for (int i = 0; i < P_NS && i < n_it; i++) {
@@ -118,153 +146,158 @@ fir_sign_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcArgs a)
 			tma_g2s_3d(ring_a + i * P_STAGE_BYTES, &tmap, 0, 8 * (s_begin + i) - 1, cg, full_a + 8 * i);
 		}
 	}
-	for (int i = tid; i < U_BMAT_BYTES / 16; i += P_THREADS) {
+	for (int i = tid; i < U_BMAT_BYTES / 16; i += P_THREADS + 32) {
 		const uint4 v = reinterpret_cast<const uint4 *>(g_umma_bmat)[i];
 		asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(bmat_a + 16 * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 	}
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	if (warp == 0) {
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(U_TMEM_COLS) : "memory");
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 	}
-
-	/* flip bit 7 of every sample of a landed stage, in place (16-byte chunks tid, tid + 128, ...: each chunk is read and
-	 * written by one thread at one address, so neither the swizzle nor any ordering between threads matters) */
-	auto flip_stage = [&](int it) {
-		const uint32_t p0 = ring_a + (it % P_NS) * P_STAGE_BYTES + 16 * tid;
-		mbar_wait(full_a + 8 * (it % P_NS), (uint32_t) ((it / P_NS) & 1));
-		if (!(a.dbg & 8)) {
-#pragma unroll
-			for (int k = 0; k < (P_STAGE_CHUNKS + P_THREADS - 1) / P_THREADS; k++)
-				if ((k + 1) * P_THREADS <= P_STAGE_CHUNKS || tid + k * P_THREADS < P_STAGE_CHUNKS) {
-					uint4 v = lds128(p0 + 16 * P_THREADS * k);
-					asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(p0 + 16 * P_THREADS * k), "r"(v.x ^ 0x00800080u),
-						     "r"(v.y ^ 0x00800080u), "r"(v.z ^ 0x00800080u), "r"(v.w ^ 0x00800080u)
-						     : "memory");
-				}
-		}
-		/* the tensor core (and the TMA request that will refill this buffer) go through the async proxy */
-		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-	};
-	auto issue_mma = [&](int it, uint32_t tmem) {
-		/* one thread: three k-steps of M128 x N96 x K32, then commit -> mbarrier */
-		const uint32_t a0 = ring_a + (it % P_NS) * P_STAGE_BYTES + 16u;
-		if (!(a.dbg & 4))
-#pragma unroll
-		for (int k = 0; k < 3; k++) {
-			const uint64_t ad = P_ADESC | (uint64_t) (((a0 + 32u * k) & 0x3FFFFu) >> 4);
-			const uint64_t bd = U_BDESC | (uint64_t) (((bmat_a + (uint32_t) (k * U_BK_BYTES)) & 0x3FFFFu) >> 4);
-			asm volatile(
-				"{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-				"tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-				::"r"(tmem), "l"(ad), "l"(bd), "r"(U_IDESC), "r"(k ? 1u : 0u), "r"(0u) : "memory");
-		}
-		asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mma_a) : "memory");
-	};
-
 	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 	__syncthreads();                              /* barriers, B matrix and the TMEM address are visible */
 	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 	const uint32_t tmem = tmem_base_s;
 
-	if (s_begin == 0) {
-		/* first stage of the tile: TMA zero-filled the block before the tile start; the carried history goes there
-		 * (samples -32..-1 = hist[4..35], src/filter.c:129-134): 16 rows x 4 chunks, written through the swizzle */
-		mbar_wait(full_a, 0u);
-		if (tid < 4 * P_CH) {
-			const int row = tid >> 2, ch = tid & 3;
-			const int16_t *h = a.st[cg + row].hist[a.hist_sel] + 4 + 8 * ch;
-			uint32_t wv[4];
-#pragma unroll
-			for (int e = 0; e < 4; e++)
-				wv[e] = (uint32_t) (uint16_t) h[2 * e] | ((uint32_t) (uint16_t) h[2 * e + 1] << 16);
-			asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(swz64(ring_a + row * P_ROW_BYTES + ch * 16)), "r"(wv[0]), "r"(wv[1]),
-				     "r"(wv[2]), "r"(wv[3])
-				     : "memory");
-		}
-		__syncthreads();
-	}
-	flip_stage(0);
-	__syncthreads();
-	if (tid == 0) {
-		asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-		issue_mma(0, tmem);
-	}
-
-	/* this thread's MMA row: channel c = m >> 3 of the group, word r = m & 7 of the stage */
-	const int m = tid, c = m >> 3, r = m & 7;
-	const int ch = cg + c;
-	const uint32_t taddr = tmem + ((uint32_t) (warp * 32) << 16);
-	uint32_t *sp = a.signs + ((int64_t) s_begin * (P_T / 32) + r) * a.n_channels + ch;
-	const int64_t sp_step = (int64_t) (P_T / 32) * a.n_channels;
-	const int16_t *grow = a.base + (int64_t) ch * a.ch_stride;
-	uint32_t qflags = 0;          /* bit 0: this thread has queued something since the last settling; bit 1: queue long enough */
-
-	for (int it = 0; it < n_it; it++) {
-		if (it + 1 < n_it)
-			flip_stage(it + 1);           /* while the tensor core works on stage `it` */
-		mbar_wait(mma_a, (uint32_t) (it & 1));
-		asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-		uint32_t word = 0;
-		if (!(a.dbg & 2))
-#pragma unroll
-		for (int h = 0; h < 2; h++) {
-			uint32_t d24[16], d16[16], d8[16], neg, clr, pend;
-			tmem_ld16(taddr + 16 * h, d24);
-			tmem_ld16(taddr + 32 + 16 * h, d16);
-			tmem_ld16(taddr + 64 + 16 * h, d8);
-			asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-			umma_half_word(d24, d16, d8, a.kc, neg, clr, pend);
-			if (pend) {    /* queued with a provisional 1; settled below, 64 at a time */
-				clr |= tc_push(pend, ((uint32_t) c << 28) | (uint32_t) ((s_begin + it) * P_T + 32 * r + 16 * h), smem_u32(&q_n),
-					       smem_u32(q_item), grow, a.st[ch].hist[a.hist_sel]);
-				qflags |= clr >> 16;
-			}
-			word |= (~(neg | clr) & 0xffffu) << (16 * h);      /* bit j = (filtered[32 w + j] > 0) */
-		}
-		*sp = word;
-		sp += sp_step;
-
-		asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-		/* the barrier: TMEM drained by every warp, stage it + 1 flipped by every thread; it also carries the decision
-		 * to settle the queue (long enough, or the CTA's last stage with something in it), so that every thread takes
-		 * the same branch */
-		const int settle = __syncthreads_or((int) ((qflags & 2u) | (it + 1 == n_it ? (qflags & 1u) : 0u)));
-		if (tid == 0) {
-			if (it + 1 < n_it) {
+	if (warp == 4) {
+		/* ===== MMA issuer + TMA refills ===== */
+		if (tid == P_THREADS) {
+			for (int it = 0; it < n_it; it++) {
+				mbar_wait(ready_a, (uint32_t) (it & 1));      /* stage `it` flipped, accumulators of stage it - 1 drained */
 				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-				issue_mma(it + 1, tmem);
-			}
-			if (it + P_NS < n_it) {
-				/* the buffer of stage `it` is free: the tensor core has read it (mma barrier above) */
-				const int b = it % P_NS;
-				mbar_expect_tx(full_a + 8 * b, (uint32_t) P_STAGE_BYTES);
-				tma_g2s_3d(ring_a + b * P_STAGE_BYTES, &tmap, 0, 8 * (s_begin + it + P_NS) - 1, cg, full_a + 8 * b);
+				const uint32_t a0 = ring_a + (it % P_NS) * P_STAGE_BYTES + 16u;
+				if (!(a.dbg & 4))
+#pragma unroll
+				for (int k = 0; k < 3; k++) {
+					const uint64_t ad = P_ADESC | (uint64_t) (((a0 + 32u * k) & 0x3FFFFu) >> 4);
+					const uint64_t bd = U_BDESC | (uint64_t) (((bmat_a + (uint32_t) (k * U_BK_BYTES)) & 0x3FFFFu) >> 4);
+					asm volatile(
+						"{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+						"tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+						::"r"(tmem), "l"(ad), "l"(bd), "r"(U_IDESC), "r"(k ? 1u : 0u), "r"(0u) : "memory");
+				}
+				asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mma_a) : "memory");
+				if (it >= 1 && it - 1 + P_NS < n_it) {
+					/* the buffer of stage it - 1 is free: the epilogue threads saw its MMAs complete before they arrived */
+					const int b = (it - 1) % P_NS;
+					mbar_expect_tx(full_a + 8 * b, (uint32_t) P_STAGE_BYTES);
+					tma_g2s_3d(ring_a + b * P_STAGE_BYTES, &tmap, 0, 8 * (s_begin + it - 1 + P_NS) - 1, cg, full_a + 8 * b);
+				}
 			}
 		}
-		if (settle) {
-			const uint32_t nq = min(q_n, (uint32_t) U_QCAP);
-			qflags = 0;
-			if ((uint32_t) tid < nq) {
-				const uint32_t item = q_item[tid];
-				const int qc = cg + (int) (item >> 28), n = (int) (item & 0x0fffffffu);
-				if (umma_resolve_global(a.base + (int64_t) qc * a.ch_stride, a.st[qc].hist[a.hist_sel], n) == 0u)
-					atomicAnd(a.signs + (int64_t) (n >> 5) * a.n_channels + qc, ~(1u << (n & 31)));
+	} else {
+		/* ===== flip + epilogue ===== */
+		/* flip bit 7 of every sample of a landed stage, in place (16-byte chunks tid, tid + 128, ...: each chunk is read
+		 * and written by one thread at one address, so neither the swizzle nor any ordering between threads matters) */
+		auto flip_stage = [&](int it) {
+			const uint32_t p0 = ring_a + (it % P_NS) * P_STAGE_BYTES + 16 * tid;
+			mbar_wait(full_a + 8 * (it % P_NS), (uint32_t) ((it / P_NS) & 1));
+			if (!(a.dbg & 8)) {
+#pragma unroll
+				for (int k = 0; k < (P_STAGE_CHUNKS + P_THREADS - 1) / P_THREADS; k++)
+					if ((k + 1) * P_THREADS <= P_STAGE_CHUNKS || tid + k * P_THREADS < P_STAGE_CHUNKS) {
+						uint4 v = lds128(p0 + 16 * P_THREADS * k);
+						asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(p0 + 16 * P_THREADS * k), "r"(v.x ^ 0x00800080u),
+							     "r"(v.y ^ 0x00800080u), "r"(v.z ^ 0x00800080u), "r"(v.w ^ 0x00800080u)
+							     : "memory");
+					}
 			}
-			__syncthreads();
-			if (tid == 0)
-				q_n = 0;
-			__syncthreads();
-		}
-	}
+			/* the tensor core (and the TMA request that will refill this buffer) go through the async proxy */
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		};
 
-	/* the tile ends in this CTA's last stage: its last 36 samples are the next tile's history (src/filter.c:129-134) */
-	if (a.save_hist && s_begin + n_it == a.n_stages && tid < P_CH) {
-		const int16_t *row = a.base + (int64_t) (cg + tid) * a.ch_stride + (int64_t) a.n_stages * P_T - GAIS_NTAPS;
+		if (s_begin == 0) {
+			/* first stage of the tile: TMA zero-filled the block before the tile start; the carried history goes there
+			 * (samples -32..-1 = hist[4..35], src/filter.c:129-134): 16 rows x 4 chunks, written through the swizzle */
+			mbar_wait(full_a, 0u);
+			if (tid < 4 * P_CH) {
+				const int row = tid >> 2, ch = tid & 3;
+				const int16_t *h = a.st[cg + row].hist[a.hist_sel] + 4 + 8 * ch;
+				uint32_t wv[4];
+#pragma unroll
+				for (int e = 0; e < 4; e++)
+					wv[e] = (uint32_t) (uint16_t) h[2 * e] | ((uint32_t) (uint16_t) h[2 * e + 1] << 16);
+				asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(swz64(ring_a + row * P_ROW_BYTES + ch * 16)), "r"(wv[0]),
+					     "r"(wv[1]), "r"(wv[2]), "r"(wv[3])
+					     : "memory");
+			}
+			epi_sync();
+		}
+		flip_stage(0);
+		mbar_arrive(ready_a);
+
+		/* this thread's MMA row: channel c = m >> 3 of the group, word r = m & 7 of the stage */
+		const int m = tid, c = m >> 3, r = m & 7;
+		const int ch = cg + c;
+		const uint32_t taddr = tmem + ((uint32_t) (warp * 32) << 16);
+		uint32_t *sp = a.signs + ((int64_t) s_begin * (P_T / 32) + r) * a.n_channels + ch;
+		const int64_t sp_step = (int64_t) (P_T / 32) * a.n_channels;
+		const int16_t *grow = a.base + (int64_t) ch * a.ch_stride;
+		uint32_t qflags = 0;          /* bit 0: this thread has queued something since the last settling */
+
+		for (int it = 0; it < n_it; it++) {
+			if (it + 1 < n_it)
+				flip_stage(it + 1);           /* while the tensor core works on stage `it` */
+			mbar_wait(mma_a, (uint32_t) (it & 1));
+			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+			uint32_t word = 0;
+			if (!(a.dbg & 2))
+#pragma unroll
+			for (int h = 0; h < 2; h++) {
+				uint32_t d24[16], d16[16], d8[16], neg, clr, pend;
+				tmem_ld16(taddr + 16 * h, d24);
+				tmem_ld16(taddr + 32 + 16 * h, d16);
+				tmem_ld16(taddr + 64 + 16 * h, d8);
+				asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+				if (h == 1) {
+					/* the accumulators are in registers and stage it + 1 is flipped: the issuer may go on */
+					asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+					mbar_arrive(ready_a);
+				}
+				umma_half_word(d24, d16, d8, a.kc, neg, clr, pend);
+				if (pend) {    /* queued with a provisional 1; settled below */
+					clr |= tc_push(pend, ((uint32_t) c << 28) | (uint32_t) ((s_begin + it) * P_T + 32 * r + 16 * h), smem_u32(&q_n),
+						       smem_u32(q_item), grow, a.st[ch].hist[a.hist_sel]);
+					qflags |= (clr >> 16) & 1u;
+				}
+				word |= (~(neg | clr) & 0xffffu) << (16 * h);      /* bit j = (filtered[32 w + j] > 0) */
+			}
+			if (a.dbg & 2)
+				mbar_arrive(ready_a);
+			*sp = word;
+			sp += sp_step;
+
+			/* every 16th stage, and after the last one, the four warps meet and settle the queue if anything is in it
+			 * (expected: one open output per stage; 128 entries; an overflow is settled on the spot in tc_push) */
+			if ((it & 15) == 15 || it + 1 == n_it) {
+				if (epi_sync_or((int) qflags)) {
+					const uint32_t nq = min(q_n, (uint32_t) U_QCAP);
+					qflags = 0;
+					if ((uint32_t) tid < nq) {
+						const uint32_t item = q_item[tid];
+						const int qc = cg + (int) (item >> 28), n = (int) (item & 0x0fffffffu);
+						if (umma_resolve_global(a.base + (int64_t) qc * a.ch_stride, a.st[qc].hist[a.hist_sel], n) == 0u)
+							atomicAnd(a.signs + (int64_t) (n >> 5) * a.n_channels + qc, ~(1u << (n & 31)));
+					}
+					epi_sync();
+					if (tid == 0)
+						q_n = 0;
+					epi_sync();
+				}
+			}
+		}
+
+		/* the tile ends in this CTA's last stage: its last 36 samples are the next tile's history (src/filter.c:129-134) */
+		if (a.save_hist && s_begin + n_it == a.n_stages && tid < P_CH) {
+			const int16_t *row = a.base + (int64_t) (cg + tid) * a.ch_stride + (int64_t) a.n_stages * P_T - GAIS_NTAPS;
 #pragma unroll 4
-		for (int i = 0; i < GAIS_NTAPS; i++)
-			a.st[cg + tid].hist[a.hist_sel ^ 1][i] = row[i];
+			for (int i = 0; i < GAIS_NTAPS; i++)
+				a.st[cg + tid].hist[a.hist_sel ^ 1][i] = row[i];
+		}
 	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 	__syncthreads();
 	if (warp == 0)
 		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(U_TMEM_COLS) : "memory");
@@ -309,7 +342,7 @@ static inline int fir_tc_launch(SampleView view, ChanState *st, int hist_sel, in
 	a.kc = g_umma_kc;
 	a.dbg = dbg;
 	dim3 grid((unsigned) (fast_ch / P_CH), (unsigned) ((a.n_stages + spb - 1) / spb));
-	fir_sign_tc_kernel<<<grid, P_THREADS, P_SMEM_BYTES, stream>>>(tm, a);
+	fir_sign_tc_kernel<<<grid, P_THREADS + 32, P_SMEM_BYTES, stream>>>(tm, a);
 	return 0;
 }
 

@@ -116,6 +116,40 @@ __global__ void save_hist_kernel(SampleView in, ChanState *st, int hist_sel, int
 		st[c].hist[hist_sel ^ 1][i] = v[i];
 }
 
+/* The level filter_run_buf() returns (src/filter.c:112-119): the maximum of the samples of the call, starting from
+ * 0 -- i.e. positive samples only, SURVEY.md H6 -- which receiver_run() turns into the "Level on ch" log line
+ * (src/receiver.c:137-147).  Optional (GAIS_KEEP_PEAK): one warp per channel, max-combined over the tiles of a run. */
+__global__ void peak_kernel(SampleView in, int n_channels, int64_t n_frames, int16_t *__restrict__ peak)
+{
+	const int c = (int) (((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+	if (c >= n_channels)
+		return;
+	const int16_t *row = in.base + (int64_t) c * in.ch_stride;
+	int m = 0;
+	if (in.t_stride == 1 && (in.ch_stride % 8) == 0 && ((uintptr_t) in.base % 16) == 0) {
+		const uint4 *v = reinterpret_cast<const uint4 *>(row);
+		for (int64_t i = lane; i < n_frames / 8; i += 32) {
+			const uint4 q = v[i];
+			const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				m = max(m, (int) (int16_t) (w[k] & 0xffffu));
+				m = max(m, (int) (int16_t) (w[k] >> 16));
+			}
+		}
+		for (int64_t n = n_frames / 8 * 8 + lane; n < n_frames; n += 32)
+			m = max(m, (int) row[n]);
+	} else {
+		for (int64_t n = lane; n < n_frames; n += 32)
+			m = max(m, (int) row[n * in.t_stride]);
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+	if (lane == 0)
+		peak[c] = (int16_t) max(m, (int) peak[c]);
+}
+
 /* ------------------------------------------------------------------------------------------
  * K2+K3.  One lane per channel, sequential in time.
  *   DPLL/slicer/NRZI: src/receiver.c:109-135.  HDLC FSM: src/protodec.c:988-1122.

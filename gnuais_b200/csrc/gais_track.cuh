@@ -142,17 +142,36 @@ __host__ __device__ inline uint32_t hdlc_nibble_entry(uint32_t id, uint32_t v)
 }
 
 /* candidate layout (64 B, same slot a gais_msg will occupy): words 0..13 stored bits (LSB first),
- * word 14 = bufferpos | stop_bit << 16 , word 15 = closing bit index */
+ * word 14 = bufferpos | stop_bit << 16 , word 15 = closing bit index.  Only frames that reach the CRC get a
+ * slot: a closing bit of 1 or bufferpos - 22 <= 0 is lostframes2 (src/protodec.c:1095-1113) whatever the
+ * bits are, and is counted by the tracker itself -- a bit stream can close such frames every ~30 bits,
+ * CRC candidates need >= 54 */
 /* everything by value: taking the address of the per-lane FSM registers would push them to local memory */
 __device__ __noinline__ uint32_t hdlc_emit(uint32_t pos, uint32_t shi, uint32_t b, uint32_t bit_index, const ChanState *s, int c,
 					   uint32_t ncand, gais_msg *slots, int slot_cap, int32_t *overflow)
 {
+	const uint32_t nw = pos >> 5, part = (pos & 31u) ? shi >> (32u - (pos & 31u)) : 0u;
 	if (ncand >= (uint32_t) slot_cap) {
-		*overflow = 1;
+		/* no slot left (only reachable with far more frames per run than AIS slots allow; the default capacity
+		 * is one candidate per 1024 samples).  The frame is still checked, here, bit by bit (src/protodec.c:106-167),
+		 * so that the COUNTERS stay the reference's; a CRC-ok frame has nowhere to go, which is what
+		 * GAIS_EOVERFLOW reports */
+		const int nbytes = (int) ((pos - 22u) >> 3) + 2;
+		uint32_t crc = 0xffffu;
+		for (int j = 0; j < nbytes * 8; j++) {
+			const uint32_t wi = (uint32_t) j >> 5, word = wi < nw ? s->store[wi] : (wi == nw ? part : 0u);
+			const uint32_t bit = (word >> (j & 31)) & 1u;
+			crc = ((crc ^ bit) & 1u) ? (crc >> 1) ^ 0x8408u : crc >> 1;
+		}
+		ChanState *sw = const_cast<ChanState *>(s);
+		if ((~crc & 0xffffu) == 0x0f47u) {
+			sw->ok++;
+			*overflow = 1;
+		} else
+			sw->crcfail++;
 		return ncand;
 	}
 	uint32_t *w = reinterpret_cast<uint32_t *>(&slots[(int64_t) c * slot_cap + ncand]);
-	const uint32_t nw = pos >> 5, part = (pos & 31u) ? shi >> (32u - (pos & 31u)) : 0u;
 #pragma unroll
 	for (uint32_t i = 0; i < 14; i++)
 		w[i] = (i < nw) ? s->store[i] : (i == nw ? part : 0u);
@@ -162,12 +181,13 @@ __device__ __noinline__ uint32_t hdlc_emit(uint32_t pos, uint32_t shi, uint32_t 
 }
 
 /* bits [i0, i1) of W one at a time (tile tails, and nibbles in which a frame outgrows the buffer) */
-struct HdlcSerialRet { HdlcRegs f; uint32_t ncand; };
+struct HdlcSerialRet { HdlcRegs f; uint32_t ncand, nsize; };
 
 __device__ __noinline__ HdlcSerialRet hdlc_bits_serial(HdlcRegs f, const uint16_t *__restrict__ tab, uint32_t W, uint32_t i0, uint32_t i1,
 						       uint32_t hb, ChanState *s, int c, uint32_t ncand, gais_msg *slots, int slot_cap,
 						       int32_t *overflow)
 {
+	uint32_t nsize = 0;
 	for (uint32_t i = i0; i < i1; i++) {
 		const uint32_t b = (W >> i) & 1u;
 		const uint32_t e = tab[f.id * 2u + b];
@@ -184,14 +204,19 @@ __device__ __noinline__ HdlcSerialRet hdlc_bits_serial(HdlcRegs f, const uint16_
 			}
 		}
 		if (e & (H_ENTER | H_EMIT)) {
-			if (e & H_EMIT)
-				ncand = hdlc_emit(f.pos, f.shi, b, hb + i, s, c, ncand, slots, slot_cap, overflow);
+			if (e & H_EMIT) {
+				if (b | (uint32_t) (f.pos <= 22u))
+					nsize++;
+				else
+					ncand = hdlc_emit(f.pos, f.shi, b, hb + i, s, c, ncand, slots, slot_cap, overflow);
+			}
 			f.pos = 0;
 		}
 	}
 	HdlcSerialRet r;
 	r.f = f;
 	r.ncand = ncand;
+	r.nsize = nsize;
 	return r;
 }
 
@@ -200,7 +225,7 @@ __device__ __noinline__ HdlcSerialRet hdlc_bits_serial(HdlcRegs f, const uint16_
  * consumed too (end of a tile) or left to the caller. Returns the number of bits consumed. */
 __device__ __forceinline__ uint32_t hdlc_chunk(HdlcRegs &f, const uint16_t *__restrict__ tab, const uint32_t *__restrict__ ntab,
 					       uint32_t W, uint32_t n, uint32_t hb, bool tail, ChanState *s, int c, uint32_t &ncand,
-					       const TrackOut &out)
+					       uint32_t &nsize, const TrackOut &out)
 {
 	const uint32_t nn = n >> 2;              /* whole nibbles */
 	const uint32_t used = tail ? n : nn * 4u;
@@ -246,6 +271,7 @@ __device__ __forceinline__ uint32_t hdlc_chunk(HdlcRegs &f, const uint16_t *__re
 								 out.overflow);   /* rare: frame outgrows the buffer */
 			f = r.f;
 			ncand = r.ncand;
+			nsize += r.nsize;
 			row = f.id << 6;
 			continue;
 		}
@@ -259,9 +285,11 @@ __device__ __forceinline__ uint32_t hdlc_chunk(HdlcRegs &f, const uint16_t *__re
 			s->store[(pos2 >> 5) - 1u] = __funnelshift_rc(f.slo, f.shi, 32u - (pos2 & 31u));
 		f.pos = pos2;
 		if (e & N_EMIT) {
-			const uint32_t p = e & 3u;
-			ncand = hdlc_emit(f.pos, f.shi, (W >> (4u * q + p)) & 1u, hb + 4u * q + p, s, c, ncand, out.slots, out.slot_cap,
-					  out.overflow);
+			const uint32_t p = e & 3u, stopbit = (W >> (4u * q + p)) & 1u;
+			if (stopbit | (uint32_t) (f.pos <= 22u))
+				nsize++;                                      /* lostframes2: nothing to check, nothing to store */
+			else
+				ncand = hdlc_emit(f.pos, f.shi, stopbit, hb + 4u * q + p, s, c, ncand, out.slots, out.slot_cap, out.overflow);
 			f.pos = 0;
 		}
 	}
@@ -270,6 +298,7 @@ __device__ __forceinline__ uint32_t hdlc_chunk(HdlcRegs &f, const uint16_t *__re
 		const HdlcSerialRet r = hdlc_bits_serial(f, tab, W, nn * 4u, used, hb, s, c, ncand, out.slots, out.slot_cap, out.overflow);
 		f = r.f;
 		ncand = r.ncand;
+		nsize += r.nsize;
 	}
 	return used;
 }
@@ -347,7 +376,7 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 	uint32_t zb = (nd << 16) | (s->pll & 0xffffu);
 	HdlcRegs f;
 	f.id = s->fsm; f.pos = s->pos; f.shi = s->cur; f.slo = s->cur2;
-	uint32_t ncand = out.run_count[c];
+	uint32_t ncand = out.run_count[c], nsize = 0;
 	const uint32_t bits_start = hb + nd;
 	const int64_t run_start = (int64_t) bits_start - (int64_t) out.run_bits[c];   /* stream index of the run's first bit */
 
@@ -379,7 +408,7 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 			const uint32_t W = ~dlo;
 			if (out.bits)
 				bits_or(out, c, (int64_t) hb - run_start, W, nd);
-			const uint32_t used = hdlc_chunk(f, tab, ntab, W, nd, hb, false, s, c, ncand, out);
+			const uint32_t used = hdlc_chunk(f, tab, ntab, W, nd, hb, false, s, c, ncand, nsize, out);
 			dlo >>= used;
 			hb += used;
 			nd -= used;
@@ -402,7 +431,7 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 		const uint32_t W = ~dlo;
 		if (out.bits)
 			bits_or(out, c, (int64_t) hb - run_start, W, nd);
-		hdlc_chunk(f, tab, ntab, W, nd, hb, true, s, c, ncand, out);
+		hdlc_chunk(f, tab, ntab, W, nd, hb, true, s, c, ncand, nsize, out);
 		dlo >>= nd;
 		hb += nd;
 		zb -= nd << 16;
@@ -414,7 +443,43 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 	s->lastbit = (uint8_t) (((prevword >> 31) ^ (dlo >> nd)) & 1u);   /* sign at the last slice */
 	s->fsm = (uint8_t) f.id; s->pos = (uint16_t) f.pos; s->cur = f.shi; s->cur2 = f.slo;
 	out.run_count[c] = ncand;
+	s->sizefail += (int32_t) nsize;
 	out.run_bits[c] += hb + (zb >> 16) - bits_start;
+}
+
+/* The HDLC half alone: protodec_decode() (src/protodec.c:988-1122) for every channel of the batch, fed with
+ * NRZI-decoded bits, one per byte (0/1), exactly what receiver_run() hands over (src/receiver.c:126-131).
+ * bits of channel c at bits[c * stride + i].  Same FSM registers, candidates and counters as track_kernel. */
+__global__ void __launch_bounds__(TRK_THREADS)
+hdlc_bits_kernel(const uint8_t *__restrict__ bits, int64_t stride, int64_t n_bits, ChanState *st, int n_channels, TrackOut out)
+{
+	__shared__ uint32_t ntab[H_NSTATES * 16];
+	__shared__ uint16_t tab[H_NSTATES * 2];
+	for (int i = threadIdx.x; i < H_NSTATES * 16; i += TRK_THREADS)
+		ntab[i] = hdlc_nibble_entry((uint32_t) i >> 4, (uint32_t) i & 15u);
+	for (int i = threadIdx.x; i < H_NSTATES * 2; i += TRK_THREADS)
+		tab[i] = (uint16_t) hdlc_transition((uint32_t) i >> 1, (uint32_t) i & 1u);
+	__syncthreads();
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= n_channels)
+		return;
+	ChanState *s = &st[c];
+	HdlcRegs f;
+	f.id = s->fsm; f.pos = s->pos; f.shi = s->cur; f.slo = s->cur2;
+	uint32_t hb = s->n_bits, ncand = out.run_count[c], nsize = 0;
+	const uint8_t *row = bits + (int64_t) c * stride;
+	for (int64_t off = 0; off < n_bits; off += 24) {
+		const uint32_t n = (uint32_t) (n_bits - off < 24 ? n_bits - off : 24);
+		uint32_t W = 0;
+		for (uint32_t i = 0; i < n; i++)
+			W |= (uint32_t) (row[off + i] & 1u) << i;
+		hb += hdlc_chunk(f, tab, ntab, W, n, hb, off + 24 >= n_bits, s, c, ncand, nsize, out);
+	}
+	s->n_bits = hb;
+	s->fsm = (uint8_t) f.id; s->pos = (uint16_t) f.pos; s->cur = f.shi; s->cur2 = f.slo;
+	s->sizefail += (int32_t) nsize;
+	out.run_count[c] = ncand;
+	out.run_bits[c] += (uint32_t) n_bits;
 }
 
 /* ---- frame check: one warp per channel, one lane per candidate ---------------------------------

@@ -37,7 +37,7 @@ class BatchReceiver:
 
     def __init__(self, n_channels: int, max_frames_per_run: int, layout: str = "planar", device: int = 0,
                  fir_mode: str = "guard", keep_bits: bool = False, keep_signs: bool = False,
-                 slot_cap: int = 0, tile_frames: int = 0, overlap=None):
+                 slot_cap: int = 0, tile_frames: int = 0, overlap=None, keep_peak: bool = False):
         self._lib = L.load()
         self._ctx = C.c_void_p()
         cfg = L.Config()
@@ -47,7 +47,7 @@ class BatchReceiver:
         cfg.layout = {"planar": L.LAYOUT_PLANAR, "interleaved": L.LAYOUT_INTERLEAVED}[layout]
         cfg.max_frames_per_run = max_frames_per_run
         cfg.fir_mode = {"guard": L.FIR_GUARD, "exact": L.FIR_EXACT}[fir_mode]
-        cfg.flags = (L.KEEP_BITS if keep_bits else 0) | (L.KEEP_SIGNS if keep_signs else 0)
+        cfg.flags = (L.KEEP_BITS if keep_bits else 0) | (L.KEEP_SIGNS if keep_signs else 0) | (L.KEEP_PEAK if keep_peak else 0)
         cfg.reserved[0] = slot_cap
         cfg.reserved[1] = tile_frames
         cfg.reserved[2] = 0 if overlap is None else (2 if overlap else 1)
@@ -119,6 +119,27 @@ class BatchReceiver:
             stride = a.shape[1] if a.shape[0] == 1 else a.strides[0] // 2
         self._keepalive = a
         L.check(self._lib.gais_run_host(self._ctx, a.ctypes.data_as(C.c_void_p), n_frames, stride))
+
+    def run_bits(self, bits, stream=None) -> None:
+        """``protodec_decode()`` for every channel (src/protodec.c:988-1122): ``bits`` is uint8 0/1, shape
+        [n_channels, n_bits] -- the NRZI-decoded bits receiver_run() would hand over -- as a numpy array / CPU
+        tensor (host path) or a CUDA torch tensor (device path)."""
+        if _is_torch(bits) and bits.is_cuda:
+            import torch
+
+            assert bits.dtype == torch.uint8 and bits.dim() == 2 and bits.shape[0] == self.n_channels
+            if stream is None:
+                stream = torch.cuda.current_stream(bits.device).cuda_stream
+            self._keepalive = bits
+            stride = bits.shape[1] if bits.shape[0] == 1 else bits.stride(0)
+            L.check(self._lib.gais_run_bits_device(self._ctx, C.c_void_p(bits.data_ptr()), bits.shape[1], stride, C.c_void_p(stream)))
+            return
+        if _is_torch(bits):
+            bits = bits.numpy()
+        a = np.ascontiguousarray(np.asarray(bits, dtype=np.uint8))
+        assert a.ndim == 2 and a.shape[0] == self.n_channels
+        self._keepalive = a
+        L.check(self._lib.gais_run_bits_host(self._ctx, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[1]))
 
     def sync(self) -> None:
         L.check(self._lib.gais_sync(self._ctx))
@@ -204,6 +225,13 @@ class BatchReceiver:
         L.check(self._lib.gais_get_signs(self._ctx, words.ctypes.data_as(C.c_void_p), words.size))
         per_ch = np.ascontiguousarray(words.T)
         return np.unpackbits(per_ch.view(np.uint8), axis=1, bitorder="little")[:, :n_frames]
+
+    def peaks(self) -> np.ndarray:
+        """Per-channel level of the last run: what filter_run_buf() returns (max of the positive samples,
+        src/filter.c:112-119); needs keep_peak."""
+        out = np.zeros(self.n_channels, dtype=np.int16)
+        L.check(self._lib.gais_get_peaks(self._ctx, out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def timing(self) -> dict:
         t = L.Timing()

@@ -67,6 +67,7 @@ enum {
 enum {
 	GAIS_KEEP_BITS = 1u << 0, /* materialise the NRZI-decoded bitstream fed to the HDLC stage */
 	GAIS_KEEP_SIGNS = 1u << 1,/* keep the FIR sign words of the last run (parity artefact) */
+	GAIS_KEEP_PEAK = 1u << 2, /* per-channel level of the last run: filter_run_buf()'s return value (src/filter.c:112-119) */
 };
 
 typedef struct gais_config {
@@ -137,6 +138,9 @@ int gais_create(const gais_config *cfg, gais_ctx **out);
 void gais_destroy(gais_ctx *ctx);
 /* back to the state right after init_receiver(): zero history, pll = 0, FSM reset, counters 0 */
 int gais_reset(gais_ctx *ctx);
+/* protodec_reset() for every channel (src/protodec.c:87-100): the HDLC bit machine goes back to ST_SKURR with an
+ * empty frame buffer; counters, seqnr, DPLL and filter history stay */
+int gais_reset_fsm(gais_ctx *ctx);
 
 /*
  * One chunk for all channels, samples already in device memory.  Asynchronous on `stream`;
@@ -148,6 +152,17 @@ int gais_run_device(gais_ctx *ctx, const int16_t *d_samples, int64_t n_frames, i
 /* Same from HOST memory (pinned or pageable): H2D copies are pipelined with the kernels. */
 int gais_run_host(gais_ctx *ctx, const int16_t *h_samples, int64_t n_frames, int64_t stride);
 int gais_sync(gais_ctx *ctx);
+
+/*
+ * The protocol half alone -- protodec_decode() (src/protodec.c:988-1122, declared src/protodec.h:76) for every
+ * channel: n_bits NRZI-decoded bits per channel, ONE PER BYTE (0/1) as receiver_run() hands them over
+ * (src/receiver.c:126-131), channel c at bits[c * stride + i].  HDLC flag hunt, de-stuffing, CRC-16, counters,
+ * message records and NMEA exactly as after gais_run_*(); the FSM state carries over between calls and may be
+ * mixed with gais_run_*() calls on the same context (the DPLL never holds bits back across a call).
+ * n_bits <= max_frames_per_run.
+ */
+int gais_run_bits_device(gais_ctx *ctx, const uint8_t *d_bits, int64_t n_bits, int64_t stride, void *stream);
+int gais_run_bits_host(gais_ctx *ctx, const uint8_t *h_bits, int64_t n_bits, int64_t stride);
 
 /* messages of the LAST run, dense, ordered by (channel, end_bit) */
 int gais_message_count(gais_ctx *ctx, int64_t *n_msgs);
@@ -175,6 +190,12 @@ int gais_get_bits(gais_ctx *ctx, uint32_t *h_words, uint32_t *h_nbits);
 /* GAIS_KEEP_SIGNS: FIR signs of the LAST run, bit j of word w of channel c = (filtered[32w+j] > 0);
  * layout [word][channel]: h_words[w * n_channels + c] */
 int gais_get_signs(gais_ctx *ctx, uint32_t *h_words, int64_t cap_words);
+
+/* GAIS_KEEP_PEAK: h_out[n_channels] = the level filter_run_buf() would have returned for the LAST run had it been
+ * one call -- max(0, largest sample): positive samples only, as the reference (src/filter.c:112-119; for a run
+ * fed in several receiver_run() chunks it is the maximum of the per-chunk values).  receiver_run() logs it as
+ * maxval / 32768 * 100 percent (src/receiver.c:137-147). */
+int gais_get_peaks(gais_ctx *ctx, int16_t *h_out);
 
 int gais_get_timing(gais_ctx *ctx, gais_timing *out);
 

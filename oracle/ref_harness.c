@@ -45,6 +45,7 @@ struct tap_ctx {
 	int64_t bits_cap, n_bits;
 	uint8_t *signs;
 	int64_t signs_cap, n_signs;
+	int peak;                /* largest value filter_run_buf() has returned (its maxval, src/filter.c:112-119) */
 };
 static __thread struct tap_ctx *tls_tap;
 
@@ -68,6 +69,8 @@ short __wrap_filter_run_buf(struct filter *f, short *in, float *out, int step, i
 {
 	short r = __real_filter_run_buf(f, in, out, step, len);
 	struct tap_ctx *t = tls_tap;
+	if (t && r > t->peak)
+		t->peak = r;
 	if (t && t->signs) {
 		for (int i = 0; i < len; i++)
 			if (t->n_signs < t->signs_cap)
@@ -252,6 +255,33 @@ int gref_run(const int16_t *buf, int64_t n_frames, int num_ch, int ch_ofs, int c
 	free_receiver(rx);
 	_mm_setcsr(csr);
 	return 0;
+}
+
+/*
+ * The level of a run: the largest value filter_run_buf() returned over the run's receiver_run() calls
+ * (src/receiver.c:107 keeps it as maxval; src/filter.c:112-119 starts each call at 0, so negative samples
+ * never count).  Tap library only; returns -1 without taps.
+ */
+int gref_peak(const int16_t *buf, int64_t n_frames, int num_ch, int ch_ofs, int chunk)
+{
+#ifdef GREF_WITH_TAPS
+	struct tap_ctx tap;
+	struct receiver *rx;
+	memset(&tap, 0, sizeof(tap));
+	tls_tap = &tap;
+	rx = init_receiver('A', num_ch, ch_ofs, NULL, NULL);
+	for (int64_t off = 0; off < n_frames; off += chunk) {
+		int len = (n_frames - off < chunk) ? (int) (n_frames - off) : chunk;
+		receiver_run(rx, (short *) (buf + off * num_ch), len);
+	}
+	fflush(stdout);
+	tls_tap = NULL;
+	free_receiver(rx);
+	return tap.peak;
+#else
+	(void) buf; (void) n_frames; (void) num_ch; (void) ch_ofs; (void) chunk;
+	return -1;
+#endif
 }
 
 /* ---- multi-threaded CPU baseline ------------------------------------------------------- */

@@ -65,6 +65,18 @@ def test_bad_arguments_rejected():
     assert lib.gais_sync(None) == -1
 
 
+@pytest.mark.skipif(not Path("/root/reference/src/receiver.h").exists(), reason="needs the reference's headers")
+def test_compat_structs_and_prototypes_match_the_reference_headers(tmp_path):
+    """tests/c/layout_check.c includes the reference's own receiver.h / protodec.h (struct tags renamed) next to
+    include/gais_compat.h: sizeof / offsetof of every field of struct receiver and struct demod_state_t, and the
+    prototypes of the seven entry points, are compile-time assertions"""
+    import subprocess
+    (tmp_path / "config.h").write_text('#define HAVE_ALSA 1\n#define PACKAGE "gnuais"\n#define VERSION "0.3.3"\n')
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-fcommon", "-I", str(tmp_path), "-I", "/root/reference/src",
+                        "-I", str(ROOT / "include"), str(ROOT / "tests" / "c" / "layout_check.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def _oracle_nmea(payload: bytes, nbits: int, seqnr: int):
     lib = O.port().lib
     lib.goracle_nmea.restype = C.c_int

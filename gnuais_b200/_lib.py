@@ -70,7 +70,7 @@ class Timing(C.Structure):
         ("track_ms", C.c_float),
         ("post_ms", C.c_float),
         ("launches", C.c_int32),
-        ("reserved", C.c_int32),
+        ("nmea_ms", C.c_float),
     ]
 
 
@@ -108,6 +108,8 @@ SYMBOLS = {
     "gais_host_free": (None, [_P]),
     "gais_device_messages": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "gais_get_nmea": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "gais_device_nmea": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "gais_get_nmea_text": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "gais_get_counters": (C.c_int, [_P, _P]),
     "gais_get_state": (C.c_int, [_P, _P]),
     "gais_get_totals": (C.c_int, [_P, C.POINTER(C.c_int64 * 3)]),

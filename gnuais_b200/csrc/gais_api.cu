@@ -75,6 +75,15 @@ struct gais_ctx {
 	int64_t dense_cap;
 	gais_nmea_rec *d_nmea;
 	int64_t nmea_cap;
+	/* packed NMEA text (gais_device_nmea) */
+	char *d_text;
+	int64_t text_cap;
+	uint64_t *d_text_off, *d_blk_off;
+	uint32_t *d_local_off, *d_blk_tot;
+	int64_t text_msgs_cap;
+	int64_t text_bytes;
+	int text_valid;
+	cudaEvent_t ev_nmea[2];
 	uint32_t *d_bits;
 	int bits_row_words;
 	int16_t *d_peak;            /* GAIS_KEEP_PEAK */
@@ -180,6 +189,9 @@ extern "C" void gais_destroy(gais_ctx *ctx)
 	cudaFree(ctx->d_offsets);
 	cudaFree(ctx->d_dense);
 	cudaFree(ctx->d_nmea);
+	cudaFree(ctx->d_text); cudaFree(ctx->d_text_off); cudaFree(ctx->d_blk_off); cudaFree(ctx->d_local_off); cudaFree(ctx->d_blk_tot);
+	for (int i = 0; i < 2; i++)
+		if (ctx->ev_nmea[i]) cudaEventDestroy(ctx->ev_nmea[i]);
 	cudaFree(ctx->d_bits);
 	cudaFree(ctx->d_peak);
 	cudaFree(ctx->d_overflow);
@@ -419,14 +431,25 @@ static int enqueue_tile(gais_ctx *ctx, SampleView view, int64_t n_frames, int ti
 	return 0;
 }
 
+static int finish(gais_ctx *ctx);
+
+/* every argument has been validated by the caller: from here on the previous run's results are gone */
 static int begin_run(gais_ctx *ctx, int64_t n_frames, cudaStream_t st)
 {
 	if (n_frames < 1 || n_frames > ctx->cfg.max_frames_per_run)
 		return fail(GAIS_EINVAL, "n_frames %lld outside 1..max_frames_per_run (%lld)", (long long) n_frames,
 			    (long long) ctx->cfg.max_frames_per_run);
 	CK(cudaSetDevice(ctx->cfg.device));
+	if (ctx->pending) {
+		/* a run that was never synced: complete it first (its kernels may still be using the per-run
+		 * buffers on another stream); its messages are superseded by this run's, an overflow it hit is not lost */
+		int rc = finish(ctx);
+		if (rc)
+			return rc;
+	}
 	ctx->launches = 0;
 	ctx->finished = 0;
+	ctx->text_valid = 0;
 	ctx->last_frames = n_frames;
 	CK(cudaMemsetAsync(ctx->d_run_count, 0, sizeof(uint32_t) * ctx->n_ch, st));
 	CK(cudaMemsetAsync(ctx->d_run_bits, 0, sizeof(uint32_t) * ctx->n_ch, st));
@@ -442,12 +465,12 @@ extern "C" int gais_run_device(gais_ctx *ctx, const int16_t *d_samples, int64_t 
 	if (!ctx || !d_samples)
 		return fail(GAIS_EINVAL, "null argument");
 	cudaStream_t st = (cudaStream_t) stream;
-	int rc = begin_run(ctx, n_frames, st);
-	if (rc)
-		return rc;
 	const bool planar = ctx->cfg.layout == GAIS_LAYOUT_PLANAR;
 	if (planar ? stride < n_frames : stride < ctx->n_ch)
 		return fail(GAIS_EINVAL, "stride %lld too small for the layout", (long long) stride);
+	int rc = begin_run(ctx, n_frames, st);
+	if (rc)
+		return rc;
 
 	int n_tiles = (int) ((n_frames + ctx->tile_frames - 1) / ctx->tile_frames);
 	if ((rc = ensure_tile_events(ctx, n_tiles)) != 0)
@@ -490,12 +513,12 @@ extern "C" int gais_run_host(gais_ctx *ctx, const int16_t *h_samples, int64_t n_
 	if (!ctx || !h_samples)
 		return fail(GAIS_EINVAL, "null argument");
 	cudaStream_t st = ctx->s_own;
-	int rc = begin_run(ctx, n_frames, st);
-	if (rc)
-		return rc;
 	const bool planar = ctx->cfg.layout == GAIS_LAYOUT_PLANAR;
 	if (planar ? stride < n_frames : stride < ctx->n_ch)
 		return fail(GAIS_EINVAL, "stride %lld too small for the layout", (long long) stride);
+	int rc = begin_run(ctx, n_frames, st);
+	if (rc)
+		return rc;
 
 	/* staging tiles: planar [n_ch][tile] (device stride = tile), interleaved [tile][stride] */
 	int64_t tile = ctx->tile_frames;
@@ -736,14 +759,104 @@ extern "C" int gais_get_nmea(gais_ctx *ctx, gais_nmea_rec *h_out, int64_t cap, i
 		return 0;
 	if (ctx->n_msgs > ctx->nmea_cap) {
 		cudaFree(ctx->d_nmea);
+	cudaFree(ctx->d_text); cudaFree(ctx->d_text_off); cudaFree(ctx->d_blk_off); cudaFree(ctx->d_local_off); cudaFree(ctx->d_blk_tot);
+	for (int i = 0; i < 2; i++)
+		if (ctx->ev_nmea[i]) cudaEventDestroy(ctx->ev_nmea[i]);
 		ctx->d_nmea = NULL;
 		ctx->nmea_cap = 0;
 		CK(cudaMalloc(&ctx->d_nmea, (size_t) ctx->n_msgs * sizeof(gais_nmea_rec)));
 		ctx->nmea_cap = ctx->n_msgs;
 	}
-	nmea_kernel<<<(unsigned) ((ctx->n_msgs + 127) / 128), 128>>>(ctx->d_dense, ctx->n_msgs, ctx->d_nmea);
+	nmea_kernel<<<(unsigned) ((ctx->n_msgs + 127) / 128), 128, 0, ctx->last_stream>>>(ctx->d_dense, ctx->n_msgs, ctx->d_nmea);
 	CK(cudaGetLastError());
-	CK(cudaMemcpy(h_out, ctx->d_nmea, (size_t) n * sizeof(gais_nmea_rec), cudaMemcpyDeviceToHost));
+	CK(cudaMemcpyAsync(h_out, ctx->d_nmea, (size_t) n * sizeof(gais_nmea_rec), cudaMemcpyDeviceToHost, ctx->last_stream));
+	CK(cudaStreamSynchronize(ctx->last_stream));
+	return 0;
+}
+
+/* packed NMEA text of the last run: lengths + block scan, scan of the block totals, one warp per message */
+static int build_text(gais_ctx *ctx)
+{
+	int rc = finish(ctx);
+	if (rc)
+		return rc;
+	if (ctx->text_valid)
+		return 0;
+	cudaStream_t st = ctx->last_stream;
+	const int64_t n = ctx->n_msgs;
+	ctx->text_bytes = 0;
+	ctx->timing.nmea_ms = 0;
+	if (n > 0) {
+		const int64_t nblk = (n + NM_BLOCK_ITEMS - 1) / NM_BLOCK_ITEMS;
+		if (n > ctx->text_msgs_cap) {
+			cudaFree(ctx->d_text_off); cudaFree(ctx->d_blk_off); cudaFree(ctx->d_local_off); cudaFree(ctx->d_blk_tot);
+			ctx->d_text_off = ctx->d_blk_off = NULL; ctx->d_local_off = ctx->d_blk_tot = NULL;
+			ctx->text_msgs_cap = 0;
+			const int64_t cap = n + n / 8 + 1024, cblk = (cap + NM_BLOCK_ITEMS - 1) / NM_BLOCK_ITEMS;
+			CK(cudaMalloc(&ctx->d_text_off, (size_t) (cap + 1) * 8));
+			CK(cudaMalloc(&ctx->d_blk_off, (size_t) (cblk + 1) * 8));
+			CK(cudaMalloc(&ctx->d_local_off, (size_t) cap * 4));
+			CK(cudaMalloc(&ctx->d_blk_tot, (size_t) cblk * 4));
+			ctx->text_msgs_cap = cap;
+		}
+		if (!ctx->ev_nmea[0]) {
+			CK(cudaEventCreate(&ctx->ev_nmea[0]));
+			CK(cudaEventCreate(&ctx->ev_nmea[1]));
+		}
+		CK(cudaEventRecord(ctx->ev_nmea[0], st));
+		nmea_len_scan_kernel<<<(unsigned) nblk, 1024, 0, st>>>(ctx->d_dense, n, ctx->d_local_off, ctx->d_blk_tot);
+		scan_counts_kernel<<<1, 1024, 0, st>>>(ctx->d_blk_tot, (int) nblk, ctx->d_blk_off);
+		uint64_t total = 0;
+		CK(cudaMemcpyAsync(&total, ctx->d_blk_off + nblk, 8, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		if ((int64_t) total > ctx->text_cap) {
+			/* a message's text is at most 2 * 82 bytes: sizing by the count would need no sync, but 3.4x the memory
+			 * of the usual 49-byte sentence; the buffer is kept, so the sync above is all a steady-state call pays */
+			cudaFree(ctx->d_text);
+			ctx->d_text = NULL;
+			ctx->text_cap = 0;
+			const int64_t cap = (int64_t) total + (int64_t) total / 8 + 4096;
+			CK(cudaMalloc(&ctx->d_text, (size_t) cap));
+			ctx->text_cap = cap;
+		}
+		nmea_write_kernel<<<(unsigned) ((n * 32 + 255) / 256), 256, 0, st>>>(ctx->d_dense, n, ctx->d_local_off, ctx->d_blk_off, ctx->d_text,
+										      ctx->d_text_off);
+		CK(cudaEventRecord(ctx->ev_nmea[1], st));
+		CK(cudaStreamSynchronize(st));
+		CK(cudaGetLastError());
+		float ms = 0;
+		CK(cudaEventElapsedTime(&ms, ctx->ev_nmea[0], ctx->ev_nmea[1]));
+		ctx->timing.nmea_ms = ms;
+		ctx->text_bytes = (int64_t) total;
+		ctx->launches += 3;
+	}
+	ctx->text_valid = 1;
+	return 0;
+}
+
+extern "C" int gais_device_nmea(gais_ctx *ctx, const char **d_text, const uint64_t **d_offsets, int64_t *n_msgs, int64_t *n_bytes)
+{
+	if (!ctx || !d_text || !d_offsets || !n_msgs || !n_bytes)
+		return fail(GAIS_EINVAL, "null argument");
+	int rc = build_text(ctx);
+	*d_text = ctx->d_text;
+	*d_offsets = ctx->d_text_off;
+	*n_msgs = ctx->n_msgs;
+	*n_bytes = ctx->text_bytes;
+	return rc;
+}
+
+extern "C" int gais_get_nmea_text(gais_ctx *ctx, char *h_text, int64_t cap, int64_t *n_bytes)
+{
+	if (!ctx || !n_bytes)
+		return fail(GAIS_EINVAL, "null argument");
+	int rc = build_text(ctx);
+	*n_bytes = ctx->text_bytes;
+	if (rc)
+		return rc;
+	const int64_t n = ctx->text_bytes < cap ? ctx->text_bytes : cap;
+	if (n > 0 && h_text)
+		CK(cudaMemcpy(h_text, ctx->d_text, (size_t) n, cudaMemcpyDeviceToHost));
 	return 0;
 }
 

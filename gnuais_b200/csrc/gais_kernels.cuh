@@ -220,7 +220,7 @@ __global__ void gather_msgs_kernel(const gais_msg *__restrict__ slots, int slot_
 		dst[i] = src[i];
 }
 
-/* K5: one thread per message */
+/* K5 (fixed-stride form, kept for gais_get_nmea): one thread per message */
 __global__ void nmea_kernel(const gais_msg *__restrict__ msgs, int64_t n, gais_nmea_rec *__restrict__ out)
 {
 	int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -233,6 +233,159 @@ __global__ void nmea_kernel(const gais_msg *__restrict__ msgs, int64_t n, gais_n
 	r->len = (uint8_t) len;
 	for (int k = 0; k < len; k++)
 		r->text[k] = text[k];
+}
+
+/* ------------------------------------------------------------------------------------------
+ * K5, packed form: the "!AIVDM...\r\n" text of all messages of a run back to back, message i at
+ * text[offsets[i] .. offsets[i+1]).  Same bytes as gn_format() (src/protodec.c:780-894, :896-929).
+ *   nmea_len_scan_kernel   length of every message's text + exclusive scan inside blocks of 4096
+ *   (scan_counts_kernel)   exclusive scan of the block totals
+ *   nmea_write_kernel      one WARP per message, one character per lane per pass, byte stores that are
+ *                          coalesced across the warp; the sentence checksum is a warp XOR reduction
+ * A sentence is  "!AIVDM,n,s,"(11) + "q,," or ",A,"(3) + <= 61 six-bit characters + ",f*hh\r\n"(7).
+ * ------------------------------------------------------------------------------------------ */
+constexpr int NM_BLOCK_ITEMS = 4096;
+
+__device__ __forceinline__ void gn_shape(const gais_msg &m, int &nch, int &nsent, int &fill)
+{
+	const int nbits = m.nbits;
+	fill = (nbits % 6) ? 6 - nbits % 6 : 0;
+	const int total = nbits + fill;
+	nch = total / 6;
+	nsent = (total <= 366) ? 1 : (total + 365) / 366;
+}
+
+__global__ void __launch_bounds__(1024)
+nmea_len_scan_kernel(const gais_msg *__restrict__ msgs, int64_t n, uint32_t *__restrict__ local_off, uint32_t *__restrict__ block_tot)
+{
+	__shared__ uint32_t warp_sums[32];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int64_t i0 = (int64_t) blockIdx.x * NM_BLOCK_ITEMS + 4 * threadIdx.x;
+	uint32_t len[4], sum = 0;
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		len[k] = 0;
+		if (i0 + k < n) {
+			/* type gate and length from the first payload byte and nbits: bytes 0 and 54..55 of the record */
+			const uint32_t w0 = *reinterpret_cast<const uint32_t *>(&msgs[i0 + k]);
+			const uint32_t w13 = reinterpret_cast<const uint32_t *>(&msgs[i0 + k])[13];
+			gais_msg m;
+			m.nbits = (uint16_t) (w13 >> 16);
+			const unsigned type = (w0 & 0xffu) >> 2;
+			if (((w13 >> 12) & 1u) && type >= 1 && type <= 24) {      /* flags bit 4: type gate passed */
+				int nch, nsent, fill;
+				gn_shape(m, nch, nsent, fill);
+				len[k] = (uint32_t) (21 * nsent + nch);
+			}
+		}
+		sum += len[k];
+	}
+	uint32_t x = sum;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+		if (lane >= d) x += y;
+	}
+	if (lane == 31) warp_sums[warp] = x;
+	__syncthreads();
+	if (warp == 0) {
+		const uint32_t ws = warp_sums[lane];
+		uint32_t xs = ws;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t y = __shfl_up_sync(0xffffffffu, xs, d);
+			if (lane >= d) xs += y;
+		}
+		warp_sums[lane] = xs - ws;
+		if (lane == 31) block_tot[blockIdx.x] = xs;
+	}
+	__syncthreads();
+	uint32_t run = warp_sums[warp] + (x - sum);
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+		if (i0 + k < n) {
+			local_off[i0 + k] = run;
+			run += len[k];
+		}
+}
+
+__global__ void __launch_bounds__(256)
+nmea_write_kernel(const gais_msg *__restrict__ msgs, int64_t n, const uint32_t *__restrict__ local_off, const uint64_t *__restrict__ block_off,
+		  char *__restrict__ text, uint64_t *__restrict__ offsets)
+{
+	const int64_t i = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int lane = threadIdx.x & 31;
+	if (i >= n)
+		return;
+	/* lanes 0..15 hold the 16 words of the record */
+	const uint32_t word = lane < 16 ? reinterpret_cast<const uint32_t *>(&msgs[i])[lane] : 0u;
+	const uint32_t w13 = __shfl_sync(0xffffffffu, word, 13), w0 = __shfl_sync(0xffffffffu, word, 0);
+	gais_msg hdr;
+	hdr.nbits = (uint16_t) (w13 >> 16);
+	const int seqnr = (int) ((w13 >> 8) & 15u), nbytes = hdr.nbits >> 3;
+	const unsigned type = (w0 & 0xffu) >> 2;
+	const bool gate = ((w13 >> 12) & 1u) && type >= 1 && type <= 24;
+	const uint64_t base = block_off[i / NM_BLOCK_ITEMS] + local_off[i];
+	if (lane == 0) {
+		offsets[i] = base;
+		if (i == n - 1) {
+			int nch = 0, nsent = 0, fill = 0;
+			if (gate) gn_shape(hdr, nch, nsent, fill);
+			offsets[n] = base + (gate ? (uint64_t) (21 * nsent + nch) : 0u);
+		}
+	}
+	if (!gate)
+		return;
+	int nch, nsent, fill;
+	gn_shape(hdr, nch, nsent, fill);
+	const int len1 = 21 + (nch < 61 ? nch : 61), len = 21 * nsent + nch;
+	char *out = text + base;
+	unsigned cs1 = 0, cs2 = 0;
+	/* pass 1: every character but the two checksum digits */
+	for (int p0 = 0; p0 < len; p0 += 32) {            /* uniform trip count: the shuffles below are warp-wide */
+		const int p = p0 + lane;
+		const bool in_range = p < len;
+		const int s = (p < len1) ? 1 : 2, q = (p < len1) ? p : p - len1;
+		const int ncs = (s == 1) ? len1 - 21 : nch - 61;
+		const int cidx = (s - 1) * 61 + (q - 14);                     /* payload character index */
+		/* the six bits at 6 * cidx, MSB first: bytes j and j + 1 of the payload (words j >> 2), zero at or beyond nbytes */
+		const int b = 6 * (cidx > 0 ? cidx : 0), j = b >> 3;
+		const uint32_t wa = __shfl_sync(0xffffffffu, word, (j >> 2) & 15), wb = __shfl_sync(0xffffffffu, word, ((j + 1) >> 2) & 15);
+		char ch = 0;
+		if (in_range) {
+			if (q < 14) {
+				const char h1[14] = { '!', 'A', 'I', 'V', 'D', 'M', ',', '0', ',', '0', ',', ',', 'A', ',' };
+				ch = h1[q];
+				if (q == 7) ch = (char) ('0' + nsent);
+				else if (q == 9) ch = (char) ('0' + s);
+				else if (nsent > 1 && q == 11) ch = (char) ('0' + seqnr);
+				else if (nsent > 1 && q == 12) ch = ',';
+			} else if (q < 14 + ncs) {
+				const unsigned ba = j < nbytes ? (wa >> (8 * (j & 3))) & 255u : 0u;
+				const unsigned bb = j + 1 < nbytes ? (wb >> (8 * ((j + 1) & 3))) & 255u : 0u;
+				const unsigned v = (((ba << 8) | bb) >> (10 - (b & 7))) & 63u;
+				ch = (char) (v < 40 ? v + 48 : v + 56);
+			} else {
+				const int t = q - 14 - ncs;                               /* ",f*hh\r\n" */
+				ch = t == 0 ? ',' : t == 1 ? (char) ('0' + ((nsent > 1 && s == nsent) ? fill : 0)) : t == 2 ? '*' : t == 5 ? '\r' : t == 6 ? '\n' : 0;
+			}
+			if (q >= 1 && q < 14 + ncs + 2) {                              /* between '!' and '*' */
+				if (s == 1) cs1 ^= (unsigned char) ch;
+				else cs2 ^= (unsigned char) ch;
+			}
+			if (ch)
+				out[p] = ch;
+		}
+	}
+	cs1 = __reduce_xor_sync(0xffffffffu, cs1);
+	cs2 = __reduce_xor_sync(0xffffffffu, cs2);
+	/* pass 2: the checksum digits, one lane each */
+	if (lane < 2 * nsent) {
+		const int s = 1 + (lane >> 1), hi = !(lane & 1);
+		const int at = (s == 1 ? 0 : len1) + 14 + ((s == 1) ? len1 - 21 : nch - 61) + 3 + (hi ? 0 : 1);
+		const unsigned cs = (s == 1) ? cs1 : cs2;
+		out[at] = gn_hex(hi ? (cs >> 4) & 15u : cs & 15u);
+	}
 }
 
 /* sum of counters over channels (3 x int64) */

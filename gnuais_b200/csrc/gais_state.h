@@ -23,10 +23,11 @@ struct ChanState {
 	/* DPLL / slicer (src/receiver.h:35-46) */
 	uint32_t pll;
 	uint8_t prev, lastbit;
-	/* HDLC FSM (src/protodec.h:44-71) */
-	uint8_t fsm, stuffed, last, nflag, nones, seqnr;
-	uint16_t nalt, pos;
-	uint32_t n_bits;                     /* NRZI bits produced since create/reset */
+	/* HDLC FSM (src/protodec.h:44-71): state id of gais_track.cuh (it folds state, nstartsign, antallpreamble,
+	 * antallenner, bitstuff and last), bufferpos, seqnr */
+	uint8_t fsm, seqnr;
+	uint16_t pos;
+	uint32_t n_bits;                     /* NRZI bits produced since create/reset, modulo 2^32 (5.2 days of audio) */
 	uint32_t dacc;                       /* NRZI difference bits sliced but not yet given to the FSM */
 	uint32_t cur, cur2;                  /* the last 64 stored frame bits (newest at bit 31 of cur) */
 	uint8_t nd, pad_[3];                 /* number of valid bits in dacc (< 24) */

@@ -225,12 +225,11 @@ __device__ __noinline__ HdlcSerialRet hdlc_bits_serial(HdlcRegs f, const uint16_
  * consumed too (end of a tile) or left to the caller. Returns the number of bits consumed. */
 __device__ __forceinline__ uint32_t hdlc_chunk(HdlcRegs &f, const uint16_t *__restrict__ tab, const uint32_t *__restrict__ ntab,
 					       uint32_t W, uint32_t n, uint32_t hb, bool tail, ChanState *s, int c, uint32_t &ncand,
-					       uint32_t &nsize, const TrackOut &out)
+					       uint32_t &nsize, const TrackOut &out, uint32_t wmask)
 {
+	/* called by all lanes of `wmask` together (the votes below are over exactly that set) */
 	const uint32_t nn = n >> 2;              /* whole nibbles */
 	const uint32_t used = tail ? n : nn * 4u;
-	if (used == 0u)
-		return 0u;
 	/* warp-uniform shortcut for idle channels: while hunting, the FSM can only move on after more
 	 * than 14 alternations ending in a 0 (src/protodec.c:1029-1037); a run-length test rules that
 	 * out exactly */
@@ -238,7 +237,7 @@ __device__ __forceinline__ uint32_t hdlc_chunk(HdlcRegs &f, const uint16_t *__re
 	uint32_t fast_id = 0;
 	/* (one vote first: with a single lane of the warp inside a frame the shortcut is off, and the
 	 * run-length test below -- ~50 instructions -- is not worth starting) */
-	if (__all_sync(__activemask(), f.id < 64u)) {
+	if (__all_sync(wmask, f.id < 64u || used == 0u)) {
 		const uint32_t leak = f.id >> 5, nalt = (f.id >> 1) & 15u, last = f.id & 1u;
 		const uint32_t vm = (used >= 32u) ? 0xffffffffu : (1u << used) - 1u;
 		const uint32_t A = (W ^ ((W << 1) | last)) & vm;          /* bit i: b_i != b_(i-1) */
@@ -247,16 +246,21 @@ __device__ __forceinline__ uint32_t hdlc_chunk(HdlcRegs &f, const uint16_t *__re
 		r &= r >> 2;
 		r &= r >> 4;
 		r &= r >> 7;                                             /* a run of >= 15 alternations inside */
-		if (nalt + L <= 14u && r == 0u) {
+		if (used == 0u) {
+			fast = true;
+			fast_id = f.id;
+		} else if (nalt + L <= 14u && r == 0u) {
 			fast = true;
 			const uint32_t n2 = (L == used) ? nalt + used : (uint32_t) __clz((int) ~(A << (32u - used)));
 			fast_id = hdlc_hunt_id(leak, n2, (W >> (used - 1u)) & 1u);
 		}
 	}
-	if (__all_sync(__activemask(), fast)) {
+	if (__all_sync(wmask, fast)) {
 		f.id = fast_id;
 		return used;
 	}
+	if (used == 0u)
+		return 0u;
 	/* the state travels through the loop as the byte offset of its table row; W2 = W << 2 puts nibble q at
 	 * bits 4q+2 .. 4q+5, where it is the entry index inside the row times 4 (the nibbles cover at most bits 0..27 of W) */
 	uint32_t row = f.id << 6;
@@ -367,6 +371,9 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 	if (c >= n_channels)
 		return;
 	ChanState *s = &st[c];
+	/* the lanes that are left walk the same number of words and take the HDLC hand-over together: every vote in
+	 * hdlc_chunk() is over exactly this set, taken outside any per-lane branch */
+	const uint32_t wmask = __activemask();
 
 	uint32_t prevword = (uint32_t) s->prev << 31;   /* bit 31 = sign of the last sample seen */
 	uint32_t dlo = s->dacc, nd = s->nd;             /* difference bits not yet given to the FSM */
@@ -378,7 +385,7 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 	f.id = s->fsm; f.pos = s->pos; f.shi = s->cur; f.slo = s->cur2;
 	uint32_t ncand = out.run_count[c], nsize = 0;
 	const uint32_t bits_start = hb + nd;
-	const int64_t run_start = (int64_t) bits_start - (int64_t) out.run_bits[c];   /* stream index of the run's first bit */
+	const uint32_t run_start = bits_start - out.run_bits[c];   /* stream index of the run's first bit (all of this modulo 2^32) */
 
 	const int n_words = (int) ((n_frames + 31) >> 5);                    /* a tile is far below 2^31 words */
 	const uint32_t *sp = signs + c;
@@ -402,13 +409,14 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 		dpll_word(x, zb, dlo);
 		zb += 32u * GAIS_PLL_INC;                /* base of the next word */
 		nd = zb >> 16;
-		if (nd >= 24u) {
-			/* at most 7 slices per 32 samples and at most 3 bits left over from the last hand-over,
-			 * so bit 31 of dlo is never reached before this point */
+		if (__any_sync(wmask, nd >= 24u)) {
+			/* some lane has 24 bits: the whole warp hands its whole nibbles over (at most 7 slices per 32 samples
+			 * and at most 3 bits left over from the last hand-over, so bit 31 of dlo is never reached before this
+			 * point) */
 			const uint32_t W = ~dlo;
-			if (out.bits)
-				bits_or(out, c, (int64_t) hb - run_start, W, nd);
-			const uint32_t used = hdlc_chunk(f, tab, ntab, W, nd, hb, false, s, c, ncand, nsize, out);
+			if (out.bits && nd >= 4u)
+				bits_or(out, c, (int64_t) (int32_t) (hb - run_start), W, nd & ~3u);
+			const uint32_t used = hdlc_chunk(f, tab, ntab, W, nd, hb, false, s, c, ncand, nsize, out, wmask);
 			dlo >>= used;
 			hb += used;
 			nd -= used;
@@ -425,13 +433,13 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 		zb += nb * GAIS_PLL_INC;
 		nd = zb >> 16;
 	}
-	if (nd) {
+	if (__any_sync(wmask, nd != 0u)) {
 		/* end of the tile: hand ALL sliced bits over now, so that FSM state, candidates and
 		 * counters at a run boundary are exactly the reference's after the same samples */
 		const uint32_t W = ~dlo;
-		if (out.bits)
-			bits_or(out, c, (int64_t) hb - run_start, W, nd);
-		hdlc_chunk(f, tab, ntab, W, nd, hb, true, s, c, ncand, nsize, out);
+		if (out.bits && nd)
+			bits_or(out, c, (int64_t) (int32_t) (hb - run_start), W, nd);
+		hdlc_chunk(f, tab, ntab, W, nd, hb, true, s, c, ncand, nsize, out, wmask);
 		dlo >>= nd;
 		hb += nd;
 		zb -= nd << 16;
@@ -464,6 +472,7 @@ hdlc_bits_kernel(const uint8_t *__restrict__ bits, int64_t stride, int64_t n_bit
 	if (c >= n_channels)
 		return;
 	ChanState *s = &st[c];
+	const uint32_t wmask = __activemask();
 	HdlcRegs f;
 	f.id = s->fsm; f.pos = s->pos; f.shi = s->cur; f.slo = s->cur2;
 	uint32_t hb = s->n_bits, ncand = out.run_count[c], nsize = 0;
@@ -473,7 +482,7 @@ hdlc_bits_kernel(const uint8_t *__restrict__ bits, int64_t stride, int64_t n_bit
 		uint32_t W = 0;
 		for (uint32_t i = 0; i < n; i++)
 			W |= (uint32_t) (row[off + i] & 1u) << i;
-		hb += hdlc_chunk(f, tab, ntab, W, n, hb, off + 24 >= n_bits, s, c, ncand, nsize, out);
+		hb += hdlc_chunk(f, tab, ntab, W, n, hb, off + 24 >= n_bits, s, c, ncand, nsize, out, wmask);
 	}
 	s->n_bits = hb;
 	s->fsm = (uint8_t) f.id; s->pos = (uint16_t) f.pos; s->cur = f.shi; s->cur2 = f.slo;

@@ -185,10 +185,18 @@ class BatchReceiver:
         return out
 
     def nmea(self) -> bytes:
-        """Concatenated ``!AIVDM...\\r\\n`` sentences of the last run, (channel, end_bit) order."""
-        recs = self.nmea_records()
-        raw = recs.view(np.uint8).reshape(-1, L.NMEA_STRIDE)
-        return b"".join(raw[i, 1:1 + raw[i, 0]].tobytes() for i in range(len(recs)))
+        """Concatenated ``!AIVDM...\\r\\n`` sentences of the last run, (channel, end_bit) order (packed on the GPU)."""
+        n = C.c_int64()
+        L.check(self._lib.gais_get_nmea_text(self._ctx, None, 0, C.byref(n)))
+        buf = np.empty(max(n.value, 1), dtype=np.uint8)
+        L.check(self._lib.gais_get_nmea_text(self._ctx, buf.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+        return buf[: n.value].tobytes()
+
+    def device_nmea(self):
+        """(text pointer, offsets pointer, n_msgs, n_bytes) of the packed NMEA text on the device."""
+        t, o, n, nb = C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
+        L.check(self._lib.gais_device_nmea(self._ctx, C.byref(t), C.byref(o), C.byref(n), C.byref(nb)))
+        return t.value or 0, o.value or 0, n.value, nb.value
 
     def counters(self) -> np.ndarray:
         out = np.zeros(self.n_channels, dtype=COUNTERS_DTYPE)
@@ -236,7 +244,7 @@ class BatchReceiver:
     def timing(self) -> dict:
         t = L.Timing()
         L.check(self._lib.gais_get_timing(self._ctx, C.byref(t)), allow=(L.E_OVERFLOW,))
-        return {k: getattr(t, k) for k in ("total_ms", "fir_ms", "track_ms", "post_ms", "launches")}
+        return {k: getattr(t, k) for k in ("total_ms", "fir_ms", "track_ms", "post_ms", "launches", "nmea_ms")}
 
 
 def nmea_format(msg) -> bytes:

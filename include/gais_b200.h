@@ -122,9 +122,9 @@ typedef struct gais_timing {
 	float total_ms;      /* first kernel start -> last kernel end (device time) */
 	float fir_ms;        /* FIR-sign kernel(s), summed over time tiles */
 	float track_ms;      /* DPLL/slicer/NRZI/HDLC/CRC kernel(s), summed */
-	float post_ms;       /* compaction (+ NMEA if requested) */
+	float post_ms;       /* frame check + compaction */
 	int32_t launches;    /* kernels launched by the call */
-	int32_t reserved;
+	float nmea_ms;       /* the last gais_device_nmea() / gais_get_nmea_text() armouring pass (0 if none) */
 } gais_timing;
 
 typedef struct gais_ctx gais_ctx;
@@ -176,6 +176,15 @@ void gais_host_free(void *h_ptr);
 int gais_device_messages(gais_ctx *ctx, const gais_msg **d_msgs, int64_t *n_msgs);
 /* NMEA text of the last run's messages, armoured on the GPU; record i belongs to message i */
 int gais_get_nmea(gais_ctx *ctx, gais_nmea_rec *h_out, int64_t cap, int64_t *n_msgs);
+
+/* The same text packed back to back, armoured by a warp per message on the run's stream: message i is
+ * d_text[d_offsets[i] .. d_offsets[i+1]) (nothing for a message the type gate dropped), n_bytes = d_offsets[n_msgs].
+ * The buffers belong to the context and are reused between runs (they grow only when a run produces more messages
+ * or text than any before it).  Bytes are those of protodec_generate_nmea() in its serial form "!%s\r\n"
+ * (src/protodec.c:780-894, :883). */
+int gais_device_nmea(gais_ctx *ctx, const char **d_text, const uint64_t **d_offsets, int64_t *n_msgs, int64_t *n_bytes);
+/* ... and copied to the host: all sentences of the last run in (channel, end_bit) order */
+int gais_get_nmea_text(gais_ctx *ctx, char *h_text, int64_t cap, int64_t *n_bytes);
 
 /* cumulative since create/reset, h_out[n_channels] */
 int gais_get_counters(gais_ctx *ctx, gais_counters *h_out);

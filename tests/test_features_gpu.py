@@ -162,3 +162,33 @@ print("same")
         env = dict(os.environ, GAIS_FIR_IMPL=impl)
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "same" in r.stdout, (impl, r.stdout[-2000:], r.stderr[-2000:])
+
+
+def test_packed_nmea_equals_fixed_records_and_host_formatter():
+    """gais_device_nmea / gais_get_nmea_text (one warp per message, packed) against the per-message formatter the host
+    shim uses and the fixed-stride records -- incl. two-sentence type 5, ungated types 25-27 and odd lengths"""
+    import torch
+    from gnuais_b200 import nmea_format
+    C_, N = 512, 96000
+    d = torch.empty((C_, N), dtype=torch.int16, device="cuda")
+    from gnuais_b200 import synth_device
+    synth_device(SynthParams(seed=55, sigma=300.0, rho=0.9), d, C_, N)
+    with BatchReceiver(C_, N) as rx:
+        rx.run(d)
+        msgs, recs = rx.messages(), rx.nmea_records()
+        text = rx.nmea()
+        tptr, optr, n, nbytes = rx.device_nmea()
+        tm = rx.timing()
+    raw = recs.view(np.uint8).reshape(-1, 176)
+    want = b"".join(raw[i, 1:1 + raw[i, 0]].tobytes() for i in range(len(recs)))
+    assert n == len(msgs) > 20000 and nbytes == len(text)
+    assert text == want
+    two = sum(1 for m in msgs[:4000] if nmea_format(m).count(b"\r\n") == 2)
+    none = sum(1 for m in msgs[:4000] if not (m["flags"] & 16))
+    assert two > 50 and none > 10
+    assert b"".join(nmea_format(m) for m in msgs[:4000]) == text[: sum(int(x) for x in raw[:4000, 0])]
+    assert tm["nmea_ms"] > 0
+    # empty run: no text
+    with BatchReceiver(16, 4096) as rx:
+        rx.run(torch.zeros((16, 4096), dtype=torch.int16, device="cuda"))
+        assert rx.nmea() == b""

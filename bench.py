@@ -45,7 +45,10 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--fir-mode", default="guard", choices=["guard", "exact"])
     ap.add_argument("--tile-frames", type=int, default=0)
-    ap.add_argument("--e2e-channels", type=int, default=4096)
+    ap.add_argument("--e2e-channels", type=int, default=8192, help="channels per GPU of the host-buffer leg (7.9 GB pinned at 480000 samples)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the cfg2 / cfg3 side measurements")
+    ap.add_argument("--no-gather-check", action="store_true")
+    ap.add_argument("--check-channels", type=int, default=256, help="channels per GPU re-run through the oracle after the timed region")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-channels-per-core", type=int, default=24)
@@ -65,7 +68,9 @@ def measured_peak():
 def ncu_traffic(kernel: str, alg_bytes: float):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
     (profiles/r1_traffic.json), scaled to this launch's algorithmic bytes; None if no capture."""
-    p = ROOT / "profiles" / "r1_traffic.json"
+    p = ROOT / "profiles" / "r2_traffic.json"
+    if not p.exists():
+        p = ROOT / "profiles" / "r1_traffic.json"
     try:
         rec = json.loads(p.read_text())[kernel]
         return rec["dram_bytes_per_launch"] * alg_bytes / rec["alg_bytes_per_launch"]
@@ -184,6 +189,124 @@ def reference_arm(args):
     return 0
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """pin this process (and, by first touch, the page-locked buffers it allocates afterwards) to the CPUs next to its
+    GPU: /sys/bus/pci/devices/<bus id>/local_cpulist.  Best effort; returns a note for the bench line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = Path("/sys/bus/pci/devices") / bus
+        cpus = set()
+        for part in (base / "local_cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "no local cpulist inside the process' affinity mask"
+        os.sched_setaffinity(0, cpus)
+        node = (base / "numa_node").read_text().strip()
+        return f"numa node {node}, {len(cpus)} cpus"
+    except Exception as e:          # containers without /sys access, one-node hosts ...
+        return f"not bound ({type(e).__name__})"
+
+
+def other_configs(args, dev, local_rank):
+    """BASELINE configs 2 and 3, measured outside the timed region (N = 1): they have one lane per channel walking the whole
+    time axis in the tracker, so they are latency-bound by construction -- reported, not optimised for."""
+    import torch
+    from gnuais_b200 import BatchReceiver, SynthParams, synth_device
+    out = {}
+    for name, n_ch, frames, layout in (("cfg2: 2 channels (AIS1+AIS2) x 2880000 samples, frame-interleaved stereo", 2, 2880000, "interleaved"),
+                                       ("cfg3: 1024 channels x 480000 samples, planar", 1024, 480000, "planar")):
+        d = torch.empty((n_ch, frames) if layout == "planar" else (frames, n_ch), dtype=torch.int16, device=dev)
+        synth_device(SynthParams(seed=args.seed, sigma=args.sigma, rho=args.rho), d, n_ch, frames, layout=layout)
+        rx = BatchReceiver(n_ch, frames, layout=layout, device=local_rank, fir_mode=args.fir_mode)
+        times = []
+        for i in range(4):
+            rx.run(d)
+            rx.sync()
+            if i:
+                times.append(rx.timing())
+        ms = sum(t["total_ms"] for t in times) / len(times)
+        out[name] = {"ms_per_run": ms, "Msamples_per_s": n_ch * frames / ms / 1e3, "fir_ms": sum(t["fir_ms"] for t in times) / len(times),
+                     "track_ms": sum(t["track_ms"] for t in times) / len(times), "msgs": rx.message_count(),
+                     "note": "latency-bound: one tracker lane per channel walks the whole time axis"}
+        rx.close()
+        del d
+    return out
+
+
+def gather_parity(args, rx, d, p, first_channel, n_ch, frames, rank, world, peer, dev):
+    """once, outside the timed region: a seeded subset of every rank's channels is regenerated on the host and run through
+    the oracle; the rank checks its own counters / DPLL+FSM state, rank 0 checks the records it GATHERED (global channel
+    numbers, canonical order, NMEA bytes) for every rank's subset, and the frame counters are summed over the ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from concurrent.futures import ThreadPoolExecutor
+    import oracle_lib as O
+    from gnuais_b200 import MSG_DTYPE, nmea_format, synth_host
+    from gnuais_b200 import dist as gdist
+
+    k = min(args.check_channels, n_ch)
+    rng = np.random.default_rng(1234 + rank)
+    subset = np.sort(rng.choice(n_ch, size=k, replace=False))
+    rx.reset()
+    rx.run(d, stream=torch.cuda.current_stream(dev).cuda_stream)
+    rx.sync()
+    cnt, st = rx.counters(), rx.state()
+
+    def one(c):
+        x = synth_host(p, 1, frames, first_channel=first_channel + int(c))[0]
+        return O.port().run(x, want_bits=False)
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+        want = list(ex.map(one, subset))
+    bad = []
+    for c, w in zip(subset, want):
+        got = (int(cnt[c]["ok"]), int(cnt[c]["crcfail"]), int(cnt[c]["sizefail"]), int(st[c]["pll"]), int(st[c]["fsm_state"]), int(st[c]["seqnr"]))
+        if got != (w.ok, w.crcfail, w.sizefail, w.pll, w.fsm_state, w.seqnr):
+            bad.append(f"rank {rank} channel {first_channel + int(c)}: counters/state {got} != oracle")
+    expect = {first_channel + int(c): w.nmea for c, w in zip(subset, want)}
+    totals = rx.totals()
+    if world > 1:
+        peer.wait_source_free()
+        peer.start(gdist.device_records(rx))
+        res = peer.finish()
+        boxes = [None] * world
+        dist.gather_object((expect, bad), boxes if rank == 0 else None, dst=0)
+        tot = gdist.reduce_totals(totals, device=dev)
+    else:
+        res = ([rx.message_count()], [gdist.device_records(rx)])
+        boxes = [(expect, bad)]
+        tot = totals
+    if rank != 0:
+        return None
+    counts, views = res
+    n_checked, n_msgs = 0, 0
+    for r in range(world):
+        exp, b = boxes[r]
+        bad += b
+        rec = views[r].cpu().numpy().view(MSG_DTYPE).reshape(-1)
+        key = rec["channel"].astype(np.int64) << 32 | rec["end_bit"]
+        if len(rec) and not np.all(np.diff(key) > 0):
+            bad.append(f"slice {r}: records not in (channel, end_bit) order")
+        if len(rec) and not (rec["channel"].min() >= r * n_ch and rec["channel"].max() < (r + 1) * n_ch):
+            bad.append(f"slice {r}: channel numbers outside the rank's range")
+        for c, text in exp.items():
+            sel = rec[rec["channel"] == c]
+            n_msgs += len(sel)
+            if b"".join(nmea_format(m) for m in sel) != text:
+                bad.append(f"slice {r}: NMEA of channel {c} differs from the oracle")
+            n_checked += 1
+    if sum(counts) != tot[0]:
+        bad.append(f"gathered {sum(counts)} records, ranks counted {tot[0]} CRC-ok frames")
+    if bad:
+        return "FAILED: " + "; ".join(bad[:5])
+    return (f"ok ({n_checked} channels of {world} rank(s) bit-exact vs oracle: counters, DPLL/FSM state, {n_msgs} gathered records -> NMEA; "
+            f"{sum(counts)} records gathered = sum of the ranks' ok counters)")
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -220,10 +343,11 @@ def main():
     synth_device(p, d, n_ch, frames, first_channel=first_channel)
     torch.cuda.synchronize()
 
-    rx = BatchReceiver(n_ch, frames, device=local_rank, fir_mode=args.fir_mode, tile_frames=args.tile_frames)
+    rx = BatchReceiver(n_ch, frames, device=local_rank, fir_mode=args.fir_mode, tile_frames=args.tile_frames,
+                       first_channel=first_channel)
     stream = torch.cuda.current_stream(dev)
-    acc = {"fir_ms": 0.0, "track_ms": 0.0, "post_ms": 0.0, "total_ms": 0.0, "launches": 0, "tiles": 0, "msgs": 0,
-           "gather_bytes": 0}
+    acc = {"fir_ms": 0.0, "track_ms": 0.0, "post_ms": 0.0, "total_ms": 0.0, "nmea_ms": 0.0, "nmea_bytes": 0, "launches": 0, "tiles": 0,
+           "msgs": 0, "gather_bytes": 0}
 
     pending = {"gather": None}
     # how the decoded records reach rank 0: by default each rank copies its slice straight into rank 0's
@@ -231,38 +355,46 @@ def main():
     gx = {"peer": None, "kind": "none (one rank)"}
     if world > 1:
         if os.environ.get("GAIS_GATHER", "peer") == "peer":
-            gx["peer"] = gdist.PeerGather(dst=0)
-            gx["kind"] = "NVLink peer copy into rank 0's buffer (CUDA IPC), counts + completion over NCCL"
+            try:
+                # a slice per rank in rank 0's buffer, sized for one message per AIS slot per channel
+                gx["peer"] = gdist.PeerGather(cap_records=n_ch * (frames // 1280 + 2), dst=0)
+                gx["kind"] = ("NVLink peer copy of each rank's records into its fixed slice of rank 0's buffer (CUDA IPC, copy engines); "
+                              "count in the slice header; nothing on the compute stream waits for another rank")
+            except gdist.PeerGatherUnavailable as e:          # raised on every rank together
+                gx["kind"] = f"NCCL point-to-point send/recv (peer mapping unavailable: {e})"
         else:
             gx["kind"] = "NCCL point-to-point send/recv of exact-size record arrays, counts over NCCL"
 
     def step(timed: bool):
+        if gx["peer"]:
+            gx["peer"].wait_source_free(stream)       # the previous step's records have left the dense array (local event)
         rx.run(d, stream=stream.cuda_stream)
         rx.sync()
+        rx.device_nmea()                              # "!AIVDM" text of every message, packed, on the run's stream
         if world > 1:
-            # collect the decoded messages on rank 0.  The transfer of step k rides NCCL's stream while
-            # step k+1 computes; it is completed before the next transfer starts and before the clock stops
-            recs = gdist.globalize_channels(gdist.device_records(rx), first_channel)
-            if pending["gather"] is not None:
-                out = pending["gather"].wait()
-                if timed and out is not None:
-                    acc["gather_bytes"] += int(out.numel())
+            # collect the decoded messages on rank 0: records already carry global channel numbers
+            recs = gdist.device_records(rx)
             if gx["peer"]:
-                try:
-                    pending["gather"] = gx["peer"].start(recs)
-                except gdist.PeerGatherUnavailable as e:      # raised on every rank together: switch transport
-                    gx["peer"], gx["kind"] = None, f"NCCL point-to-point send/recv (peer mapping unavailable: {e})"
-                    pending["gather"] = gdist.gather_records_async(recs, dst=0)
+                gx["peer"].start(recs)
+                if timed and rank == 0:
+                    acc["gather_bytes"] += int(recs.numel()) * world      # every rank moves about as much (same workload statistics)
             else:
-                pending["gather"] = gdist.gather_records_async(recs, dst=0)
+                if pending["gather"] is not None:
+                    out = pending["gather"].wait()
+                    if timed and out is not None:
+                        acc["gather_bytes"] += int(out.numel())
+                pending["gather"] = gdist.gather_records_async(recs.clone(), dst=0)
         if timed:
             tm = rx.timing()
-            for k in ("fir_ms", "track_ms", "post_ms", "total_ms"):
+            for k in ("fir_ms", "track_ms", "post_ms", "total_ms", "nmea_ms"):
                 acc[k] += tm[k]
             acc["launches"] += tm["launches"]
             acc["msgs"] += rx.message_count()
+            acc["nmea_bytes"] += rx.device_nmea()[3]
 
     def drain(timed: bool):
+        if gx["peer"]:
+            gx["peer"].finish()                       # every rank's last slice is in place on rank 0
         if pending["gather"] is not None:
             out = pending["gather"].wait()
             pending["gather"] = None
@@ -291,6 +423,9 @@ def main():
         dist.barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
+    parity = None
+    if not args.no_gather_check and (world == 1 or gx["peer"]):
+        parity = gather_parity(args, rx, d, p, first_channel, n_ch, frames, rank, world, gx["peer"], dev)
     if gx["peer"]:
         gx["peer"].close()
     if world > 1:
@@ -354,7 +489,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32/u32", "data": "synthetic",
+        "dtype": "s8 x u8 -> s32 (FIR on tcgen05 kind::i8), u32 (DPLL / HDLC / CRC)", "data": "synthetic",
         "config": {"workload": f"{n_ch} batched channels/GPU x {frames} samples (48 kHz int16, {frames / 48000:.0f} s), planar, "
                                f"synthetic GMSK seed {args.seed} sigma {args.sigma} rho {args.rho}{note}",
                    "channels_per_gpu": n_ch, "frames_per_channel": frames, "fir_mode": args.fir_mode,
@@ -363,6 +498,10 @@ def main():
         "msgs_per_s": total_msgs / (ms * 1e-3), "msgs_per_step": total_msgs / args.steps,
         "counters_rank0": {"ok": totals[0], "crcfail": totals[1], "sizefail": totals[2]},
         "roofline": roofline, "gpu_launches": acc["launches"], "clocks": clocks,
+        "nmea": {"ms_per_step": acc["nmea_ms"] / args.steps, "bytes_per_step": acc["nmea_bytes"] / args.steps,
+                 "note": "packed !AIVDM text of every message of the step, armoured on the GPU inside the timed step "
+                         "(3 launches: lengths per block, scan of block totals, one thread per message through shared memory)"},
+        "gather_parity": parity,
     }
     if world > 1:
         line["gather_bytes_per_step_rank0"] = acc["gather_bytes"] / args.steps
@@ -371,6 +510,7 @@ def main():
     # ---- end to end through the C-ABI with HOST buffers (H2D + D2H inside the timed region) ----
     if not args.no_e2e:
         e_ch = min(args.e2e_channels, n_ch)
+        numa = bind_to_gpu_numa_node(local_rank)        # before the page-locked allocation: first touch decides the node
         host = torch.empty((e_ch, frames), dtype=torch.int16, pin_memory=True)
         host.copy_(d[:e_ch])
         torch.cuda.synchronize()
@@ -396,12 +536,17 @@ def main():
             dt = float(t.item())
         line["e2e"] = {"value": e_ch * frames * world * e_steps / dt / 1e6, "unit": UNIT,
                        "h2d_bytes_per_step": 2 * e_ch * frames, "d2h_bytes_per_step": d2h // e_steps,
-                       "workload": f"{e_ch} channels/GPU x {frames} samples from pinned host memory through gais_run_host(), "
-                                   f"message records copied back to page-locked host memory every step", "steps": e_steps}
+                       "workload": f"{e_ch} channels/GPU x {frames} samples ({2 * e_ch * frames / 1e9:.1f} GB page-locked per rank) from "
+                                   f"pinned host memory through gais_run_host(), message records copied back to page-locked host "
+                                   f"memory every step; bound by the host link (PCIe H2D), not by the kernels",
+                       "steps": e_steps, "numa": numa}
         cpu_src = hv
         rxe.close()
     else:
         cpu_src = None
+
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        line["other_configs"] = other_configs(args, dev, local_rank)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

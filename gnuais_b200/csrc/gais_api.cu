@@ -79,7 +79,7 @@ struct gais_ctx {
 	char *d_text;
 	int64_t text_cap;
 	uint64_t *d_text_off, *d_blk_off;
-	uint32_t *d_local_off, *d_blk_tot;
+	uint32_t *d_blk_tot;
 	int64_t text_msgs_cap;
 	int64_t text_bytes;
 	int text_valid;
@@ -189,7 +189,7 @@ extern "C" void gais_destroy(gais_ctx *ctx)
 	cudaFree(ctx->d_offsets);
 	cudaFree(ctx->d_dense);
 	cudaFree(ctx->d_nmea);
-	cudaFree(ctx->d_text); cudaFree(ctx->d_text_off); cudaFree(ctx->d_blk_off); cudaFree(ctx->d_local_off); cudaFree(ctx->d_blk_tot);
+	cudaFree(ctx->d_text); cudaFree(ctx->d_text_off); cudaFree(ctx->d_blk_off); cudaFree(ctx->d_blk_tot);
 	for (int i = 0; i < 2; i++)
 		if (ctx->ev_nmea[i]) cudaEventDestroy(ctx->ev_nmea[i]);
 	cudaFree(ctx->d_bits);
@@ -655,7 +655,7 @@ static int finish(gais_ctx *ctx)
 	if (total > 0) {
 		int64_t threads = (int64_t) ctx->n_ch * 32;
 		gather_msgs_kernel<<<(unsigned) ((threads + 255) / 256), 256, 0, st>>>(ctx->d_slots, ctx->slot_cap, ctx->d_run_count,
-										      ctx->d_offsets, ctx->n_ch, ctx->d_dense);
+										      ctx->d_offsets, ctx->n_ch, (uint32_t) ctx->cfg.reserved[3], ctx->d_dense);
 		ctx->launches++;
 	}
 	CK(cudaEventRecord(ctx->ev[EV_POST1], st));
@@ -759,7 +759,7 @@ extern "C" int gais_get_nmea(gais_ctx *ctx, gais_nmea_rec *h_out, int64_t cap, i
 		return 0;
 	if (ctx->n_msgs > ctx->nmea_cap) {
 		cudaFree(ctx->d_nmea);
-	cudaFree(ctx->d_text); cudaFree(ctx->d_text_off); cudaFree(ctx->d_blk_off); cudaFree(ctx->d_local_off); cudaFree(ctx->d_blk_tot);
+	cudaFree(ctx->d_text); cudaFree(ctx->d_text_off); cudaFree(ctx->d_blk_off); cudaFree(ctx->d_blk_tot);
 	for (int i = 0; i < 2; i++)
 		if (ctx->ev_nmea[i]) cudaEventDestroy(ctx->ev_nmea[i]);
 		ctx->d_nmea = NULL;
@@ -774,7 +774,7 @@ extern "C" int gais_get_nmea(gais_ctx *ctx, gais_nmea_rec *h_out, int64_t cap, i
 	return 0;
 }
 
-/* packed NMEA text of the last run: lengths + block scan, scan of the block totals, one warp per message */
+/* packed NMEA text of the last run: lengths per block, scan of the block totals, one thread per message via shared memory */
 static int build_text(gais_ctx *ctx)
 {
 	int rc = finish(ctx);
@@ -789,13 +789,12 @@ static int build_text(gais_ctx *ctx)
 	if (n > 0) {
 		const int64_t nblk = (n + NM_BLOCK_ITEMS - 1) / NM_BLOCK_ITEMS;
 		if (n > ctx->text_msgs_cap) {
-			cudaFree(ctx->d_text_off); cudaFree(ctx->d_blk_off); cudaFree(ctx->d_local_off); cudaFree(ctx->d_blk_tot);
-			ctx->d_text_off = ctx->d_blk_off = NULL; ctx->d_local_off = ctx->d_blk_tot = NULL;
+			cudaFree(ctx->d_text_off); cudaFree(ctx->d_blk_off); cudaFree(ctx->d_blk_tot);
+			ctx->d_text_off = ctx->d_blk_off = NULL; ctx->d_blk_tot = NULL;
 			ctx->text_msgs_cap = 0;
 			const int64_t cap = n + n / 8 + 1024, cblk = (cap + NM_BLOCK_ITEMS - 1) / NM_BLOCK_ITEMS;
 			CK(cudaMalloc(&ctx->d_text_off, (size_t) (cap + 1) * 8));
 			CK(cudaMalloc(&ctx->d_blk_off, (size_t) (cblk + 1) * 8));
-			CK(cudaMalloc(&ctx->d_local_off, (size_t) cap * 4));
 			CK(cudaMalloc(&ctx->d_blk_tot, (size_t) cblk * 4));
 			ctx->text_msgs_cap = cap;
 		}
@@ -803,25 +802,23 @@ static int build_text(gais_ctx *ctx)
 			CK(cudaEventCreate(&ctx->ev_nmea[0]));
 			CK(cudaEventCreate(&ctx->ev_nmea[1]));
 		}
-		CK(cudaEventRecord(ctx->ev_nmea[0], st));
-		nmea_len_scan_kernel<<<(unsigned) nblk, 1024, 0, st>>>(ctx->d_dense, n, ctx->d_local_off, ctx->d_blk_tot);
-		scan_counts_kernel<<<1, 1024, 0, st>>>(ctx->d_blk_tot, (int) nblk, ctx->d_blk_off);
-		uint64_t total = 0;
-		CK(cudaMemcpyAsync(&total, ctx->d_blk_off + nblk, 8, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
-		if ((int64_t) total > ctx->text_cap) {
-			/* a message's text is at most 2 * 82 bytes: sizing by the count would need no sync, but 3.4x the memory
-			 * of the usual 49-byte sentence; the buffer is kept, so the sync above is all a steady-state call pays */
+		if (n * NM_MAX_TEXT > ctx->text_cap) {
+			/* sized by the message count (113 bytes each at most, 49 typically) so that no byte count has to come back
+			 * to the host between the kernels; kept between runs */
 			cudaFree(ctx->d_text);
 			ctx->d_text = NULL;
 			ctx->text_cap = 0;
-			const int64_t cap = (int64_t) total + (int64_t) total / 8 + 4096;
+			const int64_t cap = (n + n / 8 + 1024) * NM_MAX_TEXT;
 			CK(cudaMalloc(&ctx->d_text, (size_t) cap));
 			ctx->text_cap = cap;
 		}
-		nmea_write_kernel<<<(unsigned) ((n * 32 + 255) / 256), 256, 0, st>>>(ctx->d_dense, n, ctx->d_local_off, ctx->d_blk_off, ctx->d_text,
-										      ctx->d_text_off);
+		CK(cudaEventRecord(ctx->ev_nmea[0], st));
+		nmea_len_kernel<<<(unsigned) nblk, NM_BLOCK_ITEMS, 0, st>>>(ctx->d_dense, n, ctx->d_blk_tot);
+		scan_counts_kernel<<<1, 1024, 0, st>>>(ctx->d_blk_tot, (int) nblk, ctx->d_blk_off);
+		nmea_write_kernel<<<(unsigned) nblk, NM_BLOCK_ITEMS, 0, st>>>(ctx->d_dense, n, ctx->d_blk_off, ctx->d_text, ctx->d_text_off);
 		CK(cudaEventRecord(ctx->ev_nmea[1], st));
+		uint64_t total = 0;
+		CK(cudaMemcpyAsync(&total, ctx->d_blk_off + nblk, 8, cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
 		CK(cudaGetLastError());
 		float ms = 0;

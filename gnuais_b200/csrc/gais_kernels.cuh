@@ -206,9 +206,10 @@ scan_counts_kernel(const uint32_t *__restrict__ counts, int n, uint64_t *__restr
 	if (threadIdx.x == 0) offsets[n] = carry;
 }
 
-/* one warp per channel: copy count[c] 64-byte records, 16 B per lane */
+/* one warp per channel: copy count[c] 64-byte records, 16 B per lane; the channel field (word 14 = third word of
+ * every fourth 16-byte piece) becomes first_channel + c, the channel's number in the whole multi-GPU batch */
 __global__ void gather_msgs_kernel(const gais_msg *__restrict__ slots, int slot_cap, const uint32_t *__restrict__ counts,
-				   const uint64_t *__restrict__ offsets, int n_channels, gais_msg *__restrict__ dense)
+				   const uint64_t *__restrict__ offsets, int n_channels, uint32_t first_channel, gais_msg *__restrict__ dense)
 {
 	int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (c >= n_channels)
@@ -216,8 +217,12 @@ __global__ void gather_msgs_kernel(const gais_msg *__restrict__ slots, int slot_
 	uint32_t cnt = counts[c];
 	const uint4 *src = reinterpret_cast<const uint4 *>(slots + (int64_t) c * slot_cap);
 	uint4 *dst = reinterpret_cast<uint4 *>(dense + offsets[c]);
-	for (uint32_t i = lane; i < cnt * 4u; i += 32)
-		dst[i] = src[i];
+	for (uint32_t i = lane; i < cnt * 4u; i += 32) {
+		uint4 v = src[i];
+		if ((i & 3u) == 3u)
+			v.z += first_channel;
+		dst[i] = v;
+	}
 }
 
 /* K5 (fixed-stride form, kept for gais_get_nmea): one thread per message */
@@ -238,49 +243,36 @@ __global__ void nmea_kernel(const gais_msg *__restrict__ msgs, int64_t n, gais_n
 /* ------------------------------------------------------------------------------------------
  * K5, packed form: the "!AIVDM...\r\n" text of all messages of a run back to back, message i at
  * text[offsets[i] .. offsets[i+1]).  Same bytes as gn_format() (src/protodec.c:780-894, :896-929).
- *   nmea_len_scan_kernel   length of every message's text + exclusive scan inside blocks of 4096
+ *   nmea_len_kernel        text length of every message, summed per block of 256 messages
  *   (scan_counts_kernel)   exclusive scan of the block totals
- *   nmea_write_kernel      one WARP per message, one character per lane per pass, byte stores that are
- *                          coalesced across the warp; the sentence checksum is a warp XOR reduction
- * A sentence is  "!AIVDM,n,s,"(11) + "q,," or ",A,"(3) + <= 61 six-bit characters + ",f*hh\r\n"(7).
+ *   nmea_write_kernel      one THREAD per message writes its text into shared memory at its place inside the
+ *                          block's text (lengths scanned again inside the block); the block then copies its
+ *                          piece of the text to global memory, consecutive bytes by consecutive threads
+ * A sentence is  "!AIVDM,n,s,"(11) + "q,," or ",A,"(3) + <= 61 six-bit characters + ",f*hh\r\n"(7); a message is
+ * at most two sentences (426 payload bits).
  * ------------------------------------------------------------------------------------------ */
-constexpr int NM_BLOCK_ITEMS = 4096;
+constexpr int NM_BLOCK_ITEMS = 256;
+constexpr int NM_MAX_TEXT = 2 * 21 + 71;            /* 113 bytes per message at most */
 
-__device__ __forceinline__ void gn_shape(const gais_msg &m, int &nch, int &nsent, int &fill)
+/* words 0 and 13 of a record: type gate and text length (0 when the gate drops the message) */
+__device__ __forceinline__ uint32_t gn_text_len(uint32_t w0, uint32_t w13, int &nch, int &nsent, int &fill)
 {
-	const int nbits = m.nbits;
+	const int nbits = (int) (w13 >> 16);
+	const unsigned type = (w0 & 0xffu) >> 2;
 	fill = (nbits % 6) ? 6 - nbits % 6 : 0;
 	const int total = nbits + fill;
 	nch = total / 6;
-	nsent = (total <= 366) ? 1 : (total + 365) / 366;
+	nsent = (total <= 366) ? 1 : 2;
+	if (!((w13 >> 12) & 1u) || type < 1 || type > 24 || nch > 71)      /* flags bit 4: type gate passed */
+		return 0u;
+	return (uint32_t) (21 * nsent + nch);
 }
 
-__global__ void __launch_bounds__(1024)
-nmea_len_scan_kernel(const gais_msg *__restrict__ msgs, int64_t n, uint32_t *__restrict__ local_off, uint32_t *__restrict__ block_tot)
+/* inclusive scan of one value per thread over a block of 256; returns the exclusive prefix, *total = block sum */
+__device__ __forceinline__ uint32_t block_scan_256(uint32_t v, uint32_t *warp_sums /* [8] shared */, uint32_t *total)
 {
-	__shared__ uint32_t warp_sums[32];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int64_t i0 = (int64_t) blockIdx.x * NM_BLOCK_ITEMS + 4 * threadIdx.x;
-	uint32_t len[4], sum = 0;
-#pragma unroll
-	for (int k = 0; k < 4; k++) {
-		len[k] = 0;
-		if (i0 + k < n) {
-			/* type gate and length from the first payload byte and nbits: bytes 0 and 54..55 of the record */
-			const uint32_t w0 = *reinterpret_cast<const uint32_t *>(&msgs[i0 + k]);
-			const uint32_t w13 = reinterpret_cast<const uint32_t *>(&msgs[i0 + k])[13];
-			gais_msg m;
-			m.nbits = (uint16_t) (w13 >> 16);
-			const unsigned type = (w0 & 0xffu) >> 2;
-			if (((w13 >> 12) & 1u) && type >= 1 && type <= 24) {      /* flags bit 4: type gate passed */
-				int nch, nsent, fill;
-				gn_shape(m, nch, nsent, fill);
-				len[k] = (uint32_t) (21 * nsent + nch);
-			}
-		}
-		sum += len[k];
-	}
-	uint32_t x = sum;
+	uint32_t x = v;
 #pragma unroll
 	for (int d = 1; d < 32; d <<= 1) {
 		const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
@@ -288,104 +280,110 @@ nmea_len_scan_kernel(const gais_msg *__restrict__ msgs, int64_t n, uint32_t *__r
 	}
 	if (lane == 31) warp_sums[warp] = x;
 	__syncthreads();
-	if (warp == 0) {
-		const uint32_t ws = warp_sums[lane];
-		uint32_t xs = ws;
+	uint32_t base = 0, tot = 0;
 #pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const uint32_t y = __shfl_up_sync(0xffffffffu, xs, d);
-			if (lane >= d) xs += y;
-		}
-		warp_sums[lane] = xs - ws;
-		if (lane == 31) block_tot[blockIdx.x] = xs;
+	for (int w = 0; w < NM_BLOCK_ITEMS / 32; w++) {
+		const uint32_t ws = warp_sums[w];
+		if (w < warp) base += ws;
+		tot += ws;
 	}
-	__syncthreads();
-	uint32_t run = warp_sums[warp] + (x - sum);
-#pragma unroll
-	for (int k = 0; k < 4; k++)
-		if (i0 + k < n) {
-			local_off[i0 + k] = run;
-			run += len[k];
-		}
+	*total = tot;
+	return base + x - v;
 }
 
-__global__ void __launch_bounds__(256)
-nmea_write_kernel(const gais_msg *__restrict__ msgs, int64_t n, const uint32_t *__restrict__ local_off, const uint64_t *__restrict__ block_off,
-		  char *__restrict__ text, uint64_t *__restrict__ offsets)
+__global__ void __launch_bounds__(NM_BLOCK_ITEMS)
+nmea_len_kernel(const gais_msg *__restrict__ msgs, int64_t n, uint32_t *__restrict__ block_tot)
 {
-	const int64_t i = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const int lane = threadIdx.x & 31;
-	if (i >= n)
-		return;
-	/* lanes 0..15 hold the 16 words of the record */
-	const uint32_t word = lane < 16 ? reinterpret_cast<const uint32_t *>(&msgs[i])[lane] : 0u;
-	const uint32_t w13 = __shfl_sync(0xffffffffu, word, 13), w0 = __shfl_sync(0xffffffffu, word, 0);
-	gais_msg hdr;
-	hdr.nbits = (uint16_t) (w13 >> 16);
-	const int seqnr = (int) ((w13 >> 8) & 15u), nbytes = hdr.nbits >> 3;
-	const unsigned type = (w0 & 0xffu) >> 2;
-	const bool gate = ((w13 >> 12) & 1u) && type >= 1 && type <= 24;
-	const uint64_t base = block_off[i / NM_BLOCK_ITEMS] + local_off[i];
-	if (lane == 0) {
-		offsets[i] = base;
-		if (i == n - 1) {
-			int nch = 0, nsent = 0, fill = 0;
-			if (gate) gn_shape(hdr, nch, nsent, fill);
-			offsets[n] = base + (gate ? (uint64_t) (21 * nsent + nch) : 0u);
+	__shared__ uint32_t warp_sums[NM_BLOCK_ITEMS / 32];
+	const int64_t i = (int64_t) blockIdx.x * NM_BLOCK_ITEMS + threadIdx.x;
+	uint32_t len = 0;
+	if (i < n) {
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(&msgs[i]);
+		int nch, nsent, fill;
+		len = gn_text_len(w[0], w[13], nch, nsent, fill);
+	}
+	uint32_t tot;
+	block_scan_256(len, warp_sums, &tot);
+	if (threadIdx.x == 0)
+		block_tot[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(NM_BLOCK_ITEMS)
+nmea_write_kernel(const gais_msg *__restrict__ msgs, int64_t n, const uint64_t *__restrict__ block_off, char *__restrict__ text,
+		  uint64_t *__restrict__ offsets)
+{
+	__shared__ uint32_t warp_sums[NM_BLOCK_ITEMS / 32];
+	__shared__ __align__(16) char buf[NM_BLOCK_ITEMS * NM_MAX_TEXT];
+	const int64_t i = (int64_t) blockIdx.x * NM_BLOCK_ITEMS + threadIdx.x;
+	uint32_t w[14], len = 0;
+	int nch = 0, nsent = 0, fill = 0;
+	if (i < n) {
+		/* the record: four 16-byte loads, a warp reads 2 KB of consecutive records */
+		const uint4 *src = reinterpret_cast<const uint4 *>(&msgs[i]);
+		const uint4 a = src[0], b = src[1], c = src[2], d = src[3];
+		w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+		w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w; w[12] = d.x; w[13] = d.y;
+		len = gn_text_len(w[0], w[13], nch, nsent, fill);
+	}
+	uint32_t tot;
+	const uint32_t at = block_scan_256(len, warp_sums, &tot);
+	const uint64_t base = block_off[blockIdx.x];
+	if (i < n) {
+		offsets[i] = base + at;
+		if (i == n - 1)
+			offsets[n] = base + at + len;
+	}
+	if (len) {
+		const int nbytes = (int) (w[13] >> 16) >> 3, seqnr = (int) ((w[13] >> 8) & 15u);
+		w[13] &= 0xffu;                      /* payload byte 52; bytes at or beyond nbytes read as 0 below */
+		char *o = buf + at;
+		int ci = 0;                          /* payload character index */
+		for (int s = 1; s <= nsent; s++) {
+			unsigned cs = 0;
+			const int ncs = (s == 1) ? (nch < 61 ? nch : 61) : nch - 61;
+#define NM_PUT(ch_) do { const char c_ = (char) (ch_); *o++ = c_; cs ^= (unsigned char) c_; } while (0)
+			*o++ = '!';
+			NM_PUT('A'); NM_PUT('I'); NM_PUT('V'); NM_PUT('D'); NM_PUT('M'); NM_PUT(',');
+			NM_PUT('0' + nsent); NM_PUT(','); NM_PUT('0' + s); NM_PUT(',');
+			if (nsent > 1) { NM_PUT('0' + seqnr); NM_PUT(','); NM_PUT(','); }
+			else { NM_PUT(','); NM_PUT('A'); NM_PUT(','); }
+			/* 24 payload bits = 3 bytes = 4 characters at a time; byte j of the payload is byte j & 3 of word j >> 2 */
+#pragma unroll
+			for (int g = 0; g < 18; g++) {
+				if (4 * g + 3 < ci || 4 * g >= ci + ncs)
+					continue;                       /* group outside this sentence */
+				unsigned v24 = 0;
+#pragma unroll
+				for (int k = 0; k < 3; k++) {
+					const int j = 3 * g + k;
+					const unsigned byte = (j < nbytes) ? (w[j >> 2] >> (8 * (j & 3))) & 255u : 0u;
+					v24 = (v24 << 8) | byte;
+				}
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					const int cidx = 4 * g + k;
+					if (cidx >= ci && cidx < ci + ncs) {
+						const unsigned v = (v24 >> (18 - 6 * k)) & 63u;
+						NM_PUT(v < 40 ? v + 48 : v + 56);
+					}
+				}
+			}
+			ci += ncs;
+			NM_PUT(',');
+			NM_PUT('0' + ((nsent > 1 && s == nsent) ? fill : 0));
+#undef NM_PUT
+			*o++ = '*';
+			*o++ = gn_hex((cs >> 4) & 15u);
+			*o++ = gn_hex(cs & 15u);
+			*o++ = '\r';
+			*o++ = '\n';
 		}
 	}
-	if (!gate)
-		return;
-	int nch, nsent, fill;
-	gn_shape(hdr, nch, nsent, fill);
-	const int len1 = 21 + (nch < 61 ? nch : 61), len = 21 * nsent + nch;
-	char *out = text + base;
-	unsigned cs1 = 0, cs2 = 0;
-	/* pass 1: every character but the two checksum digits */
-	for (int p0 = 0; p0 < len; p0 += 32) {            /* uniform trip count: the shuffles below are warp-wide */
-		const int p = p0 + lane;
-		const bool in_range = p < len;
-		const int s = (p < len1) ? 1 : 2, q = (p < len1) ? p : p - len1;
-		const int ncs = (s == 1) ? len1 - 21 : nch - 61;
-		const int cidx = (s - 1) * 61 + (q - 14);                     /* payload character index */
-		/* the six bits at 6 * cidx, MSB first: bytes j and j + 1 of the payload (words j >> 2), zero at or beyond nbytes */
-		const int b = 6 * (cidx > 0 ? cidx : 0), j = b >> 3;
-		const uint32_t wa = __shfl_sync(0xffffffffu, word, (j >> 2) & 15), wb = __shfl_sync(0xffffffffu, word, ((j + 1) >> 2) & 15);
-		char ch = 0;
-		if (in_range) {
-			if (q < 14) {
-				const char h1[14] = { '!', 'A', 'I', 'V', 'D', 'M', ',', '0', ',', '0', ',', ',', 'A', ',' };
-				ch = h1[q];
-				if (q == 7) ch = (char) ('0' + nsent);
-				else if (q == 9) ch = (char) ('0' + s);
-				else if (nsent > 1 && q == 11) ch = (char) ('0' + seqnr);
-				else if (nsent > 1 && q == 12) ch = ',';
-			} else if (q < 14 + ncs) {
-				const unsigned ba = j < nbytes ? (wa >> (8 * (j & 3))) & 255u : 0u;
-				const unsigned bb = j + 1 < nbytes ? (wb >> (8 * ((j + 1) & 3))) & 255u : 0u;
-				const unsigned v = (((ba << 8) | bb) >> (10 - (b & 7))) & 63u;
-				ch = (char) (v < 40 ? v + 48 : v + 56);
-			} else {
-				const int t = q - 14 - ncs;                               /* ",f*hh\r\n" */
-				ch = t == 0 ? ',' : t == 1 ? (char) ('0' + ((nsent > 1 && s == nsent) ? fill : 0)) : t == 2 ? '*' : t == 5 ? '\r' : t == 6 ? '\n' : 0;
-			}
-			if (q >= 1 && q < 14 + ncs + 2) {                              /* between '!' and '*' */
-				if (s == 1) cs1 ^= (unsigned char) ch;
-				else cs2 ^= (unsigned char) ch;
-			}
-			if (ch)
-				out[p] = ch;
-		}
-	}
-	cs1 = __reduce_xor_sync(0xffffffffu, cs1);
-	cs2 = __reduce_xor_sync(0xffffffffu, cs2);
-	/* pass 2: the checksum digits, one lane each */
-	if (lane < 2 * nsent) {
-		const int s = 1 + (lane >> 1), hi = !(lane & 1);
-		const int at = (s == 1 ? 0 : len1) + 14 + ((s == 1) ? len1 - 21 : nch - 61) + 3 + (hi ? 0 : 1);
-		const unsigned cs = (s == 1) ? cs1 : cs2;
-		out[at] = gn_hex(hi ? (cs >> 4) & 15u : cs & 15u);
-	}
+	__syncthreads();
+	/* the block's text leaves as one contiguous piece: consecutive bytes by consecutive threads */
+	char *dst = text + base;
+	for (uint32_t k = threadIdx.x; k < tot; k += NM_BLOCK_ITEMS)
+		dst[k] = buf[k];
 }
 
 /* sum of counters over channels (3 x int64) */

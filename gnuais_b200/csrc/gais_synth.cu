@@ -10,37 +10,12 @@
 #include "gais_b200.h"
 #include "synth_core.h"
 
-static gais_synth_params to_params(const gais_synth *p)
-{
-	gais_synth_params q;
-	q.seed = p->seed;
-	q.amplitude = p->amplitude;
-	q.noise_q16 = p->noise_q16;
-	q.rho_q16 = p->rho_q16;
-	q.jitter = p->jitter;
-	return q;
-}
+#include "synth_host_impl.h"
 
 extern "C" int gais_synth_host(const gais_synth *p, uint32_t first_channel, int32_t n_channels, int64_t n_frames,
 			       int16_t *h_out, int32_t layout, int64_t stride)
 {
-	if (!p || !h_out || n_channels < 1 || n_frames < 1)
-		return GAIS_EINVAL;
-	gais_synth_params q = to_params(p);
-	const int64_t ch_stride = (layout == GAIS_LAYOUT_PLANAR) ? stride : 1;
-	const int64_t t_stride = (layout == GAIS_LAYOUT_PLANAR) ? 1 : stride;
-	for (int32_t c = 0; c < n_channels; c++) {
-		uint32_t ck = gs_channel_key(q.seed, first_channel + (uint32_t) c);
-		int16_t *row = h_out + (int64_t) c * ch_stride;
-		for (int64_t n0 = 0; n0 < n_frames; n0 += GS_PAIR_SAMPLES) {
-			gs_burst b[2];
-			gs_build_pair(b, ck, (uint32_t) (n0 / GS_PAIR_SAMPLES), &q);
-			int64_t lim = (n_frames - n0 < GS_PAIR_SAMPLES) ? n_frames - n0 : GS_PAIR_SAMPLES;
-			for (int64_t m = 0; m < lim; m++)
-				row[(n0 + m) * t_stride] = gs_sample(b, ck, (uint32_t) (n0 + m), (int32_t) m, &q);
-		}
-	}
-	return 0;
+	return gs_fill_host(p, first_channel, n_channels, n_frames, h_out, layout, stride);
 }
 
 /* one warp per (channel, slot pair): lane 0 builds the bursts in shared memory, all lanes
@@ -74,7 +49,7 @@ extern "C" int gais_synth_device(const gais_synth *p, uint32_t first_channel, in
 {
 	if (!p || !d_out || n_channels < 1 || n_frames < 1)
 		return GAIS_EINVAL;
-	gais_synth_params q = to_params(p);
+	gais_synth_params q = gs_to_params(p);
 	const int64_t ch_stride = (layout == GAIS_LAYOUT_PLANAR) ? stride : 1;
 	const int64_t t_stride = (layout == GAIS_LAYOUT_PLANAR) ? 1 : stride;
 	const int64_t n_pairs = (n_frames + GS_PAIR_SAMPLES - 1) / GS_PAIR_SAMPLES;

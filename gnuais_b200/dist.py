@@ -131,27 +131,45 @@ class PeerGatherUnavailable(RuntimeError):
     """raised on EVERY rank of the group when the CUDA IPC mapping cannot be set up"""
 
 
-class PeerGather:
-    """Collect every rank's records on `dst` WITHOUT a collective on the payload: `dst` owns a receive
-    buffer, every other rank maps it through CUDA IPC and copies its records straight into its slice
-    over NVLink with one cudaMemcpyAsync on a side stream (copy engines: no SMs, no NCCL proxy, so
-    the next step's kernels keep the GPU while the records move).  NCCL carries only the per-rank
-    counts (8 bytes each) and a one-word completion all-reduce.
+HDR_BYTES = REC_BYTES      # slice header: int64 count, int64 step, 48 bytes unused
 
-    One box only (CUDA IPC); needs the `cuda-python` bindings.  The buffer grows on demand: every rank
-    sees the same counts, so every rank takes the same (re)allocation branch.
+
+class PeerGather:
+    """Collect every rank's records on `dst` with NO collective and NO count exchange on the critical path.
+
+    `dst` owns one receive buffer of `world` fixed-capacity SLICES (64-byte header + cap_records records);
+    every other rank maps it through CUDA IPC.  Per step a rank copies its (channel, end_bit)-ordered records
+    -- which already carry global channel numbers (gais_config.reserved[3]) -- straight into ITS slice over
+    NVLink with cudaMemcpyAsync on a side stream (copy engines: no SMs, no NCCL proxy), then the header
+    {count, step}.  Nothing on the compute stream ever waits for another rank: the only thing it waits for
+    is the local "source has been read" event before the next run overwrites the dense array.  A one-word
+    NCCL all-reduce rides the SIDE stream after each copy, so that step k is complete on `dst` before any
+    rank's step k + 1 transfer starts; ranks are otherwise free to drift apart by a step.
+
+    One box only (CUDA IPC); needs the `cuda-python` bindings.
     """
 
-    def __init__(self, dst: int = 0, group=None):
+    def __init__(self, cap_records: int, dst: int = 0, group=None):
         from cuda.bindings import runtime as rt   # noqa: F401  (fail here, not in the middle of a step)
 
         self._rt = rt
         self.group, self.dst = group, dst
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.device = torch.device("cuda", torch.cuda.current_device())
-        self.ptr, self.cap = 0, 0
+        self.cap = int(cap_records)
+        self.slice_bytes = HDR_BYTES + self.cap * REC_BYTES
+        self.ptr = 0
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._work = None
+        self._copied = None
+        self._keep = None
+        self.step = 0
+        # headers in flight: a small ring, so that step k + 1 never rewrites the words step k's copy is still reading
+        self._hdr_host = torch.zeros((8, 8), dtype=torch.int64).pin_memory()
+        self._hdr_dev = torch.zeros((8, 8), dtype=torch.int64, device=self.device)
+        self._hdr_done = [None] * 8
+        self._allocate()
 
     @staticmethod
     def _ck(res, what):
@@ -160,25 +178,13 @@ class PeerGather:
             raise RuntimeError(f"{what} failed: CUDA error {int(err)}")
         return res[1] if isinstance(res, tuple) and len(res) > 1 else None
 
-    def _release(self):
+    def _allocate(self):
         rt = self._rt
-        if self.ptr:
-            torch.cuda.synchronize(self.device)
-            if self.rank == self.dst:
-                dist.barrier(group=self.group)          # nobody still has it mapped for writing
-                self._ck(rt.cudaFree(self.ptr), "cudaFree")
-            else:
-                self._ck(rt.cudaIpcCloseMemHandle(self.ptr), "cudaIpcCloseMemHandle")
-                dist.barrier(group=self.group)
-        self.ptr, self.cap = 0, 0
-
-    def _allocate(self, cap_records: int):
-        rt = self._rt
-        self._release()
-        nbytes = cap_records * REC_BYTES
+        nbytes = self.world * self.slice_bytes
         blob = None
         if self.rank == self.dst:
             self.ptr = int(self._ck(rt.cudaMalloc(nbytes), "cudaMalloc"))
+            self._ck(rt.cudaMemset(self.ptr, 0, nbytes), "cudaMemset")
             blob = bytes(self._ck(rt.cudaIpcGetMemHandle(self.ptr), "cudaIpcGetMemHandle").reserved)
         box = [blob]
         dist.broadcast_object_list(box, src=self.dst, group=self.group)
@@ -201,42 +207,76 @@ class PeerGather:
             dist.barrier(group=self.group)               # every rank, whether its own mapping worked or not
             if self.rank == self.dst:
                 rt.cudaFree(self.ptr)
-            self.ptr, self.cap = 0, 0
+            self.ptr = 0
             raise PeerGatherUnavailable("cudaIpcOpenMemHandle failed on at least one rank")
-        self.cap = cap_records
 
-    def start(self, records: torch.Tensor) -> "PendingGather":
-        """Enqueue the collection of `records` ([n, 64] uint8, a private copy with global channel
-        numbers).  Returns at once; wait() gives the concatenation on dst (a view of the receive buffer,
-        valid until the next start()), None elsewhere."""
+    def wait_source_free(self, stream=None):
+        """make `stream` (default: the current one) wait until the last start()'s copy has read its source"""
+        if self._copied is not None:
+            (stream or torch.cuda.current_stream(self.device)).wait_event(self._copied)
+
+    def start(self, records: torch.Tensor) -> None:
+        """Enqueue the transfer of `records` ([n, 64] uint8 on this device, global channel numbers) into this rank's
+        slice.  Returns at once; `records` must stay untouched until wait_source_free() / finish()."""
         rt = self._rt
-        n_local = torch.tensor([records.shape[0]], dtype=torch.int64, device=self.device)
-        counts = torch.zeros(self.world, dtype=torch.int64, device=self.device)
-        dist.all_gather_into_tensor(counts, n_local, group=self.group)
-        counts = counts.cpu().tolist()
-        offs = [0]
-        for c in counts:
-            offs.append(offs[-1] + c)
-        total = offs[-1]
-        if total > self.cap:
-            self._allocate(total + total // 4 + 1024)
-        records = records.contiguous()
+        n = int(records.shape[0])
+        if n > self.cap:
+            raise RuntimeError(f"rank {self.rank}: {n} records exceed the slice capacity {self.cap}")
+        self.step += 1
+        k = self.step % 8
+        if self._hdr_done[k] is not None:
+            self._hdr_done[k].synchronize()       # eight steps back: long done unless the side stream is stuck
+        self._hdr_host[k, 0], self._hdr_host[k, 1] = n, self.step
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream(self.device))
+        base = self.ptr + self.rank * self.slice_bytes
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(ready)
-            if counts[self.rank] > 0:
-                self._ck(rt.cudaMemcpyAsync(self.ptr + offs[self.rank] * REC_BYTES, records.data_ptr(),
-                                            counts[self.rank] * REC_BYTES, rt.cudaMemcpyKind.cudaMemcpyDefault,
+            if self._work is not None:
+                self._work.wait()                 # step k - 1 is complete on dst (side stream only)
+            if n > 0:
+                self._ck(rt.cudaMemcpyAsync(base + HDR_BYTES, records.data_ptr(), n * REC_BYTES, rt.cudaMemcpyKind.cudaMemcpyDefault,
                                             self.copy_stream.cuda_stream), "cudaMemcpyAsync (peer)")
-            # every rank enters this after its own copy has completed on its stream, so once it is
-            # done on dst all slices are in place
-            work = dist.all_reduce(self._flag, group=self.group, async_op=True)
-        out = None
-        if self.rank == self.dst:
-            out = (torch.as_tensor(_CudaView(self.ptr, total * REC_BYTES), device=self.device).view(total, REC_BYTES)
-                   if total else torch.empty((0, REC_BYTES), dtype=torch.uint8, device=self.device))
-        return PendingGather([work], out, records)
+            self._hdr_dev[k].copy_(self._hdr_host[k], non_blocking=True)
+            self._ck(rt.cudaMemcpyAsync(base, self._hdr_dev[k].data_ptr(), HDR_BYTES, rt.cudaMemcpyKind.cudaMemcpyDefault,
+                                        self.copy_stream.cuda_stream), "cudaMemcpyAsync (peer header)")
+            self._copied = torch.cuda.Event()
+            self._copied.record(self.copy_stream)
+            self._hdr_done[k] = self._copied
+            self._work = dist.all_reduce(self._flag, group=self.group, async_op=True)
+        self._keep = records
+
+    def finish(self):
+        """Complete everything in flight.  On dst: (counts per rank, list of per-rank [count, 64] uint8 views of the
+        slices -- valid until the next start()); None elsewhere."""
+        with torch.cuda.stream(self.copy_stream):
+            if self._work is not None:
+                self._work.wait()
+                self._work = None
+        self.copy_stream.synchronize()
+        self._keep = None
+        if self.rank != self.dst:
+            return None
+        counts, views = [], []
+        for r in range(self.world):
+            base = self.ptr + r * self.slice_bytes
+            hdr = torch.as_tensor(_CudaView(base, HDR_BYTES), device=self.device).view(torch.int64).cpu()
+            n = int(hdr[0])
+            counts.append(n)
+            views.append(torch.as_tensor(_CudaView(base + HDR_BYTES, max(n, 1) * REC_BYTES), device=self.device)[: n * REC_BYTES]
+                         .view(n, REC_BYTES))
+        return counts, views
 
     def close(self):
-        self._release()
+        rt = self._rt
+        if not self.ptr:
+            return
+        self.finish()
+        torch.cuda.synchronize(self.device)
+        if self.rank == self.dst:
+            dist.barrier(group=self.group)          # nobody still has it mapped for writing
+            self._ck(rt.cudaFree(self.ptr), "cudaFree")
+        else:
+            self._ck(rt.cudaIpcCloseMemHandle(self.ptr), "cudaIpcCloseMemHandle")
+            dist.barrier(group=self.group)
+        self.ptr = 0

@@ -37,7 +37,7 @@ class BatchReceiver:
 
     def __init__(self, n_channels: int, max_frames_per_run: int, layout: str = "planar", device: int = 0,
                  fir_mode: str = "guard", keep_bits: bool = False, keep_signs: bool = False,
-                 slot_cap: int = 0, tile_frames: int = 0, overlap=None, keep_peak: bool = False):
+                 slot_cap: int = 0, tile_frames: int = 0, overlap=None, keep_peak: bool = False, first_channel: int = 0):
         self._lib = L.load()
         self._ctx = C.c_void_p()
         cfg = L.Config()
@@ -51,8 +51,10 @@ class BatchReceiver:
         cfg.reserved[0] = slot_cap
         cfg.reserved[1] = tile_frames
         cfg.reserved[2] = 0 if overlap is None else (2 if overlap else 1)
+        cfg.reserved[3] = first_channel
         L.check(self._lib.gais_create(C.byref(cfg), C.byref(self._ctx)))
         self.n_channels = n_channels
+        self.first_channel = first_channel
         self.layout = layout
         self.max_frames_per_run = max_frames_per_run
         self._keepalive = None

@@ -33,17 +33,37 @@ class SynthParams:
         return s
 
 
+_synth_lib = None
+
+
+def _host_lib():
+    """libgais_synth.so: the generator alone (plain C).  Loading it maps nothing of the product, so the reference arm
+    of bench.py and the CPU tests can synthesise audio without touching libgaisb200.so."""
+    global _synth_lib
+    if _synth_lib is None:
+        path = L.LIB_PATH.parent / "libgais_synth.so"
+        if not path.exists():
+            raise ImportError(f"{path} is missing: run __graft_entry__.build()")
+        lib = C.CDLL(str(path))
+        lib.gais_synth_host.restype = C.c_int
+        lib.gais_synth_host.argtypes = [C.POINTER(L.Synth), C.c_uint32, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_int64]
+        _synth_lib = lib
+    return _synth_lib
+
+
 def synth_host(p: SynthParams, n_channels: int, n_frames: int, first_channel: int = 0, layout: str = "planar",
                stride: int | None = None) -> np.ndarray:
     """int16 array, planar [n_channels, n_frames] or interleaved [n_frames, n_channels]; no GPU needed."""
-    lib = L.load()
+    lib = _host_lib()
     planar = layout == "planar"
     if stride is None:
         stride = n_frames if planar else n_channels
     out = np.zeros((n_channels, stride) if planar else (n_frames, stride), dtype=np.int16)
     s = p.c_struct()
-    L.check(lib.gais_synth_host(C.byref(s), first_channel, n_channels, n_frames, out.ctypes.data_as(C.c_void_p),
-                                L.LAYOUT_PLANAR if planar else L.LAYOUT_INTERLEAVED, stride))
+    rc = lib.gais_synth_host(C.byref(s), first_channel, n_channels, n_frames, out.ctypes.data_as(C.c_void_p),
+                             L.LAYOUT_PLANAR if planar else L.LAYOUT_INTERLEAVED, stride)
+    if rc != 0:
+        raise ValueError(f"gais_synth_host failed: {rc}")
     return out
 
 

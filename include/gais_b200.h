@@ -80,7 +80,9 @@ typedef struct gais_config {
 	uint32_t flags;             /* GAIS_KEEP_* */
 	int32_t reserved[8];        /* tuning knobs, 0 = library default:
 	                               [0] message slots per channel per run, [1] time-tile length in frames,
-	                               [2] FIR/tracking overlap across tiles (1 = off, 2 = on); [3..7] must be 0 */
+	                               [2] FIR/tracking overlap across tiles (1 = off, 2 = on),
+	                               [3] number of this context's channel 0 in a batch sharded over several contexts /
+	                                   GPUs: gais_msg.channel = reserved[3] + local index; [4..7] must be 0 */
 } gais_config;
 
 /* One CRC-ok HDLC frame, 64 bytes.  payload[j] is byte j of the frame as the reference packs
@@ -91,7 +93,7 @@ typedef struct gais_msg {
 	uint8_t  flags;       /* bits 0-3: seqnr the reference holds when it formats this frame (0..9);
 	                         bit 4: type gate passed (1 <= type <= 24 -> NMEA is emitted) */
 	uint16_t nbits;       /* bufferpos - 22 of src/protodec.c:1096 (payload bits incl. a ragged tail) */
-	uint32_t channel;     /* channel index inside the batch */
+	uint32_t channel;     /* channel index inside the batch (+ gais_config.reserved[3] when the batch is sharded) */
 	uint32_t end_bit;     /* index of the NRZI bit that closed the frame, counted per channel since create/reset */
 } gais_msg;
 

@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--no-gather-check", action="store_true")
     ap.add_argument("--check-channels", type=int, default=256, help="channels per GPU re-run through the oracle after the timed region")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-two-kernel", action="store_true", help="skip the side measurement of the two-kernel path (GAIS_FUSED=0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-channels-per-core", type=int, default=24)
     return ap.parse_args()
@@ -438,9 +439,10 @@ def main():
     else:
         total_msgs = acc["msgs"]
 
-    tile_frames = rx_tile_frames(n_ch, args.tile_frames)
-    overlap = os.environ.get("GAIS_OVERLAP", "1") != "0" and frames > tile_frames
-    plan = rx_tile_plan(frames, tile_frames, overlap)       # samples per FIR / tracking launch, in order
+    fused = fused_path(n_ch, args.fir_mode)
+    tile_frames = FUSED_MAX_FRAMES if fused else rx_tile_frames(n_ch, args.tile_frames)
+    overlap = not fused and os.environ.get("GAIS_OVERLAP", "1") != "0" and frames > tile_frames
+    plan = rx_tile_plan(frames, tile_frames, overlap)       # samples per launch of the chain, in order
     n_tiles = len(plan)
     samples_per_step = n_ch * frames * world
     value = samples_per_step * args.steps / (ms * 1e-3) / 1e6
@@ -451,11 +453,18 @@ def main():
     # algorithmic bytes of ALL launches of the timed region over the sum of their durations
     peak, peak_src = measured_peak()
     fir_step, trk_step = acc["fir_ms"] / args.steps, acc["track_ms"] / args.steps
-    dom = "fir_sign" if fir_step >= trk_step else "track"
-    step_ms_dom = max(fir_step, trk_step)
-    # algorithmic bytes: 2 B per input sample for the kernel that reads the audio;
-    # 64 B per emitted record belongs to the tracking kernel
-    alg_step = 2.0 * n_ch * frames if dom == "fir_sign" else 2.0 * n_ch * frames + 64.0 * acc["msgs"] / args.steps
+    msgs_step = acc["msgs"] / args.steps
+    if fused:
+        # ONE kernel does FIR sign + DPLL + NRZI + HDLC (gais_fused.cuh); the library's "fir" events bracket it, the "track" events
+        # bracket the sweep-up kernels of a ragged tile end (none at this shape)
+        dom, step_ms_dom = "ais_fused", fir_step
+        # algorithmic bytes: 2 B per input sample read + 64 B per frame candidate written
+        alg_step = 2.0 * n_ch * frames + 64.0 * msgs_step
+    else:
+        dom = "fir_sign" if fir_step >= trk_step else "track"
+        step_ms_dom = max(fir_step, trk_step)
+        # 2 B per input sample for the kernel that reads the audio; 64 B per emitted record belongs to the tracking kernel
+        alg_step = 2.0 * n_ch * frames if dom == "fir_sign" else 2.0 * n_ch * frames + 64.0 * msgs_step
     alg_bytes = alg_step / n_tiles
     launch_ms = step_ms_dom / n_tiles
     achieved = alg_step / (step_ms_dom * 1e-3) / 1e9
@@ -467,8 +476,36 @@ def main():
                              "include the other kernel's share of the SMs (see solo)" if overlap else ""),
                 "chain": {"fir_ms_per_step": acc["fir_ms"] / args.steps, "track_ms_per_step": acc["track_ms"] / args.steps,
                           "post_ms_per_step": acc["post_ms"] / args.steps,
-                          "whole_chain_GBps": (2.0 * n_ch * frames + 64.0 * acc["msgs"] / args.steps)
+                          "whole_chain_GBps": (2.0 * n_ch * frames + 64.0 * msgs_step)
                           / (acc["total_ms"] / args.steps * 1e-3) / 1e9}}
+    if fused:
+        roofline["chain"] = {"fused_kernel_ms_per_step": fir_step, "ragged_end_kernels_ms_per_step": trk_step,
+                             "frame_check_scan_gather_ms_per_step": acc["post_ms"] / args.steps,
+                             "whole_chain_GBps": alg_step / (acc["total_ms"] / args.steps * 1e-3) / 1e9,
+                             "note": "one launch per step: FIR sign (tcgen05 kind::i8), DPLL, slicer, NRZI and the HDLC bit machine in one "
+                                     "persistent kernel, sign words handed over in shared memory; bound by integer instruction issue "
+                                     "(ALU pipe), not by HBM: see DESIGN.md"}
+        if world == 1 and not args.no_two_kernel:
+            # the same workload through the two-kernel path (GAIS_FUSED=0: FIR-sign kernel -> sign words in HBM -> tracking
+            # kernel), outside the timed region: 1 warm-up + 2 steps
+            os.environ["GAIS_FUSED"] = "0"
+            try:
+                rx2 = BatchReceiver(n_ch, frames, device=local_rank, fir_mode=args.fir_mode, tile_frames=args.tile_frames)
+                two = {"total_ms": 0.0, "fir_ms": 0.0, "track_ms": 0.0}
+                for i in range(3):
+                    rx2.run(d, stream=stream.cuda_stream)
+                    rx2.sync()
+                    if i:
+                        tm = rx2.timing()
+                        for k2 in two:
+                            two[k2] += tm[k2] / 2
+                two["msgs"] = rx2.message_count()
+                rx2.close()
+                roofline["two_kernel_path"] = {"ms_per_step": two["total_ms"], "fir_ms_per_step": two["fir_ms"],
+                                               "track_ms_per_step": two["track_ms"], "msgs": two["msgs"],
+                                               "note": "GAIS_FUSED=0, FIR of tile t+1 overlapped with tracking of tile t"}
+            finally:
+                del os.environ["GAIS_FUSED"]
     if overlap:
         # the same kernels timed alone (overlap off), outside the timed region: 1 warm-up + 2 steps
         rxs = BatchReceiver(n_ch, frames, device=local_rank, fir_mode=args.fir_mode, tile_frames=args.tile_frames, overlap=False)
@@ -493,7 +530,7 @@ def main():
         "config": {"workload": f"{n_ch} batched channels/GPU x {frames} samples (48 kHz int16, {frames / 48000:.0f} s), planar, "
                                f"synthetic GMSK seed {args.seed} sigma {args.sigma} rho {args.rho}{note}",
                    "channels_per_gpu": n_ch, "frames_per_channel": frames, "fir_mode": args.fir_mode,
-                   "tile_frames": tile_frames, "parallelism": f"channels sharded x{world}, no data-path collective",
+                   "tile_frames": min(tile_frames, frames), "chain": "fused (one kernel)" if fused else "two kernels", "parallelism": f"channels sharded x{world}, no data-path collective",
                    "l2": f"input {2 * n_ch * frames / 1e9:.1f} GB per GPU >> 126 MB L2: no flush needed between steps"},
         "msgs_per_s": total_msgs / (ms * 1e-3), "msgs_per_step": total_msgs / args.steps,
         "counters_rank0": {"ok": totals[0], "crcfail": totals[1], "sizefail": totals[2]},
@@ -581,6 +618,16 @@ def plan_summary(plan):
         out.append(f"{j - i}x{plan[i]}" if j - i > 1 else str(plan[i]))
         i = j
     return " + ".join(out)
+
+
+FUSED_MAX_FRAMES = 1 << 22       # gais_fused.cuh X_MAX_FRAMES: samples per launch of the fused kernel
+
+
+def fused_path(n_ch: int, fir_mode: str) -> bool:
+    """mirror of the library's choice (gais_api.cu fused_part): the one-kernel chain takes planar, aligned input whose
+    channel count is a multiple of 32, in guard mode, unless GAIS_FUSED=0 or an older FIR is selected for an A/B run"""
+    return (fir_mode == "guard" and n_ch % 32 == 0 and os.environ.get("GAIS_FUSED", "1") != "0"
+            and os.environ.get("GAIS_FIR_IMPL", "") in ("", "tc"))
 
 
 def rx_tile_frames(n_ch: int, requested: int) -> int:

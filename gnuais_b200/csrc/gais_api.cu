@@ -22,6 +22,7 @@
 #include "gais_fir_umma.cuh"
 #include "gais_fir_tc.cuh"
 #include "gais_track.cuh"
+#include "gais_fused.cuh"
 
 using namespace gais;
 
@@ -93,7 +94,9 @@ struct gais_ctx {
 	int64_t stage_elems;
 	cudaStream_t s_copy, s_own, s_fir, s_trk;
 	cudaEvent_t ev_fir_done[2], ev_trk_done[2], ev_join;
-	int overlap;                /* GAIS_OVERLAP=1: FIR of tile t+1 concurrent with tracking of tile t */
+	int overlap;                /* GAIS_OVERLAP=1: FIR of tile t+1 concurrent with tracking of tile t (two-kernel path only) */
+	int fused;                  /* GAIS_FUSED=1 (default): the one-kernel chain of gais_fused.cuh wherever the input allows it */
+	int n_sms;
 	cudaEvent_t ev[EV_COUNT], ev_copy[2], ev_free[2];
 	cudaEvent_t *ev_tile;       /* 4 per tile: fir start, fir end, track start, track end */
 	int ev_tile_cap;
@@ -275,14 +278,14 @@ extern "C" int gais_create(const gais_config *cfg, gais_ctx **out)
 
 	{
 		int64_t run_frames = cfg->max_frames_per_run;
+		ctx->fused = (int) env_i64("GAIS_FUSED", 1) && fir_impl() == 2;
+		ctx->n_sms = prop.multiProcessorCount;
 		if (cfg->flags & GAIS_KEEP_SIGNS) {
 			ctx->sign_words = ((run_frames + tile - 1) / tile) * (tile / 32);
 			CKC(cudaMalloc(&ctx->d_signs[0], (size_t) ctx->sign_words * ctx->n_ch * 4));
-		} else {
-			ctx->sign_words = tile / 32;
-			CKC(cudaMalloc(&ctx->d_signs[0], (size_t) ctx->sign_words * ctx->n_ch * 4));
-			CKC(cudaMalloc(&ctx->d_signs[1], (size_t) ctx->sign_words * ctx->n_ch * 4));
 		}
+		/* otherwise the sign-word buffers of the two-kernel path are allocated by the first run that needs them
+		 * (ensure_signs): the fused kernel keeps the sign words in shared memory */
 		ctx->slot_cap = cfg->reserved[0] > 0 ? cfg->reserved[0] : (int) (run_frames / 1280 + run_frames / 5120 + 8);
 		CKC(cudaMalloc(&ctx->d_state, (size_t) ctx->n_ch * sizeof(ChanState)));
 		CKC(cudaMalloc(&ctx->d_slots, (size_t) ctx->n_ch * ctx->slot_cap * sizeof(gais_msg)));
@@ -323,7 +326,7 @@ extern "C" int gais_create(const gais_config *cfg, gais_ctx **out)
 	}
 	if ((rc = upload_taps()) != 0)
 		goto bad;
-	if ((rc = fir_setup()) != 0 || (rc = fir_umma_setup()) != 0 || (rc = fir_tc_setup(cfg->device)) != 0) {
+	if ((rc = fir_setup()) != 0 || (rc = fir_umma_setup()) != 0 || (rc = fir_tc_setup(cfg->device)) != 0 || (rc = fused_setup()) != 0) {
 		rc = fail(GAIS_ECUDA, "fir_setup failed: %s", cudaGetErrorString(cudaGetLastError()));
 		goto bad;
 	}
@@ -378,30 +381,106 @@ static int enqueue_post(gais_ctx *ctx, cudaStream_t st)
 	return 0;
 }
 
-/* enqueue FIR + tracking for one time tile whose samples are at `view` (n = 0 is the first
- * sample of the tile) */
+/* which part of a tile the fused kernel takes: channels [0, ch) x samples [0, frames) (0, 0: none) */
+struct FusedPart { int ch; int64_t frames; };
+
+static FusedPart fused_part(const gais_ctx *ctx, const SampleView &view, int64_t n_frames)
+{
+	FusedPart p = { 0, 0 };
+	const bool aligned = ctx->cfg.layout == GAIS_LAYOUT_PLANAR && view.t_stride == 1 && (view.ch_stride % 8) == 0 &&
+			     ((uintptr_t) view.base % 16) == 0;
+	if (ctx->fused && ctx->cfg.fir_mode == GAIS_FIR_GUARD && aligned && n_frames <= X_MAX_FRAMES) {
+		p.ch = ctx->n_ch / 32 * 32;
+		p.frames = n_frames / P_T * P_T;
+		if (p.ch == 0 || p.frames == 0)
+			p.ch = 0, p.frames = 0;
+	}
+	return p;
+}
+
+/* sign words per channel a tile needs in global memory: what the fused kernel does not take */
+static int64_t tile_sign_words(const gais_ctx *ctx, const FusedPart &fp, int64_t n_frames)
+{
+	if (fp.ch == ctx->n_ch)
+		return (n_frames - fp.frames + 31) / 32;
+	return (n_frames + 31) / 32;
+}
+
+/* the two sign-word buffers of the two-kernel path, [words][n_ch] each, grown on demand (not with GAIS_KEEP_SIGNS:
+ * that buffer is run-sized from the start) */
+static int ensure_signs(gais_ctx *ctx, int64_t words)
+{
+	if ((ctx->cfg.flags & GAIS_KEEP_SIGNS) || words <= ctx->sign_words)
+		return 0;
+	CK(cudaDeviceSynchronize());
+	cudaFree(ctx->d_signs[0]);
+	cudaFree(ctx->d_signs[1]);
+	ctx->d_signs[0] = ctx->d_signs[1] = NULL;
+	ctx->sign_words = 0;
+	for (int i = 0; i < 2; i++) {
+		cudaError_t e = cudaMalloc(&ctx->d_signs[i], (size_t) words * ctx->n_ch * 4);
+		if (e != cudaSuccess) {
+			cudaGetLastError();
+			return fail(e == cudaErrorMemoryAllocation ? GAIS_ENOMEM : GAIS_ECUDA, "sign-word buffer (%lld words x %d channels): %s",
+				    (long long) words, ctx->n_ch, cudaGetErrorString(e));
+		}
+	}
+	ctx->sign_words = words;
+	return 0;
+}
+
+/* enqueue the chain for one time tile whose samples are at `view` (n = 0 is the first sample of the tile).
+ * The fused kernel (gais_fused.cuh) takes whole channel sets and whole 256-sample stages of aligned planar
+ * input; the FIR-sign and tracking kernels sweep up what is left (ragged end of the tile, channels beyond a
+ * multiple of 32) and everything else (interleaved or unaligned input, GAIS_FIR_EXACT, GAIS_FUSED=0). */
 static int enqueue_tile(gais_ctx *ctx, SampleView view, int64_t n_frames, int tile_idx, int64_t word_ofs, cudaStream_t st,
 			cudaStream_t st_trk, bool timed)
 {
-	/* st carries the FIR stage, st_trk the tracking stage.  When they differ (overlap mode) the
-	 * FIR of tile t+1 runs while tile t is being tracked; the two sign buffers are handed back and
+	/* st carries the FIR stage, st_trk the tracking stage.  When they differ (overlap mode of the two-kernel
+	 * path) the FIR of tile t+1 runs while tile t is being tracked; the two sign buffers are handed back and
 	 * forth with events. */
 	const bool overlap = st != st_trk;
 	const bool keep = (ctx->cfg.flags & GAIS_KEEP_SIGNS) != 0;
+	const FusedPart fp = overlap ? FusedPart{ 0, 0 } : fused_part(ctx, view, n_frames);
 	uint32_t *signs;
 	if (keep)
 		signs = ctx->d_signs[0] + word_ofs * ctx->n_ch;
-	else
+	else {
+		/* when the fused kernel takes every channel, only the words after its last stage exist in global memory */
 		signs = ctx->d_signs[tile_idx & 1];
+		if (fp.ch == ctx->n_ch && signs)
+			signs -= (fp.frames / 32) * ctx->n_ch;
+	}
+	TrackOut out = make_out(ctx);
 
 	if (overlap && !keep && tile_idx >= 2)
 		CK(cudaStreamWaitEvent(st, ctx->ev_trk_done[tile_idx & 1], 0));   /* buffer still being read by tile t-2 */
 	if (timed) CK(cudaEventRecord(ctx->ev_tile[4 * tile_idx + 0], st));
-	int hist_saved = 0;
-	int nl = fir_launch(ctx->cfg.fir_mode, ctx->cfg.layout, view, ctx->d_state, ctx->hist_sel, ctx->n_ch, n_frames, signs, st, &hist_saved);
-	if (nl < 0)
-		return fail(GAIS_ECUDA, "FIR launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-	ctx->launches += nl;
+	int hist_saved = 0, nl;
+	if (fp.ch) {
+		nl = fused_launch(view, ctx->d_state, ctx->hist_sel, ctx->n_ch, fp.ch, fp.frames, fp.frames == n_frames ? 1 : 0,
+				  keep ? signs : NULL, out, ctx->n_sms, st);
+		if (nl < 0)
+			return fail(GAIS_ECUDA, "fused launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+		ctx->launches += nl;
+		hist_saved = fp.frames == n_frames ? fp.ch : 0;
+		/* FIR signs of what is left: the ragged end of the fused channels, and the other channels */
+		if (fp.frames < n_frames) {
+			dim3 grid((unsigned) ((fp.ch + K1_CH - 1) / K1_CH), (unsigned) ((n_frames - fp.frames + K1_TILE - 1) / K1_TILE));
+			fir_sign_exact_kernel<<<grid, K1_CH * 32, 0, st>>>(view, ctx->d_state, ctx->hist_sel, 0, fp.ch, fp.frames, n_frames, ctx->n_ch, signs);
+			ctx->launches++;
+		}
+		if (fp.ch < ctx->n_ch) {
+			dim3 grid((unsigned) ((ctx->n_ch - fp.ch + K1_CH - 1) / K1_CH), (unsigned) ((n_frames + K1_TILE - 1) / K1_TILE));
+			fir_sign_exact_kernel<<<grid, K1_CH * 32, 0, st>>>(view, ctx->d_state, ctx->hist_sel, fp.ch, ctx->n_ch, 0, n_frames, ctx->n_ch, signs);
+			ctx->launches++;
+		}
+	} else {
+		nl = fir_launch(ctx->cfg.fir_mode, ctx->cfg.layout, view, ctx->d_state, ctx->hist_sel, ctx->n_ch, n_frames, signs, st, &hist_saved);
+		if (nl < 0)
+			return fail(GAIS_ECUDA, "FIR launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+		ctx->launches += nl;
+	}
 	if (hist_saved < ctx->n_ch) {
 		save_hist_kernel<<<(ctx->n_ch - hist_saved + 127) / 128, 128, 0, st>>>(view, ctx->d_state, ctx->hist_sel, hist_saved, ctx->n_ch,
 										    n_frames);
@@ -419,11 +498,25 @@ static int enqueue_tile(gais_ctx *ctx, SampleView view, int64_t n_frames, int ti
 	}
 
 	if (timed) CK(cudaEventRecord(ctx->ev_tile[4 * tile_idx + 2], st_trk));
-	TrackOut out = make_out(ctx);
-	nl = track_launch(signs, ctx->d_state, ctx->n_ch, n_frames, out, st_trk);
-	if (nl < 0)
-		return fail(GAIS_ECUDA, "tracking launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-	ctx->launches += nl;
+	if (fp.ch) {
+		if (fp.frames < n_frames) {
+			nl = track_launch(signs + (fp.frames / 32) * ctx->n_ch, ctx->d_state, 0, fp.ch, ctx->n_ch, n_frames - fp.frames, out, st_trk);
+			if (nl < 0)
+				return fail(GAIS_ECUDA, "tracking launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+			ctx->launches += nl;
+		}
+		if (fp.ch < ctx->n_ch) {
+			nl = track_launch(signs, ctx->d_state, fp.ch, ctx->n_ch, ctx->n_ch, n_frames, out, st_trk);
+			if (nl < 0)
+				return fail(GAIS_ECUDA, "tracking launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+			ctx->launches += nl;
+		}
+	} else {
+		nl = track_launch(signs, ctx->d_state, 0, ctx->n_ch, ctx->n_ch, n_frames, out, st_trk);
+		if (nl < 0)
+			return fail(GAIS_ECUDA, "tracking launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+		ctx->launches += nl;
+	}
 	if (timed) CK(cudaEventRecord(ctx->ev_tile[4 * tile_idx + 3], st_trk));
 	if (overlap)
 		CK(cudaEventRecord(ctx->ev_trk_done[tile_idx & 1], st_trk));
@@ -472,24 +565,45 @@ extern "C" int gais_run_device(gais_ctx *ctx, const int16_t *d_samples, int64_t 
 	if (rc)
 		return rc;
 
-	int n_tiles = (int) ((n_frames + ctx->tile_frames - 1) / ctx->tile_frames);
+	/* tile plan.  Where the fused kernel takes every channel there is nothing to stage between kernels, so a tile is
+	 * as long as one launch may be; otherwise the sign words of a tile go through global memory (ctx->tile_frames) */
+	SampleView v0;
+	v0.ch_stride = planar ? stride : 1;
+	v0.t_stride = planar ? 1 : stride;
+	v0.base = d_samples;
+	int64_t tile = ctx->tile_frames;
+	const bool keep = (ctx->cfg.flags & GAIS_KEEP_SIGNS) != 0;
+	const FusedPart fp0 = fused_part(ctx, v0, n_frames < tile ? n_frames : tile);
+	const bool fused_all = fp0.ch == ctx->n_ch && !keep;
+	if (fused_all)
+		tile = X_MAX_FRAMES;
+	int n_tiles = (int) ((n_frames + tile - 1) / tile);
 	if ((rc = ensure_tile_events(ctx, n_tiles)) != 0)
 		return rc;
+	{
+		const int64_t nf0 = n_frames < tile ? n_frames : tile;
+		int64_t words = tile_sign_words(ctx, fused_part(ctx, v0, nf0), nf0);
+		if (n_tiles > 1) {
+			const int64_t nfl = n_frames - (int64_t) (n_tiles - 1) * tile, wl = tile_sign_words(ctx, fused_part(ctx, v0, nfl), nfl);
+			if (wl > words)
+				words = wl;
+		}
+		if ((rc = ensure_signs(ctx, words)) != 0)
+			return rc;
+	}
 	CK(cudaEventRecord(ctx->ev[EV_START], st));
-	/* overlap mode: FIR on s_fir, tracking on the high-priority s_trk, both forked from / joined to st */
+	/* overlap mode (two-kernel path only): FIR on s_fir, tracking on the high-priority s_trk, both forked from / joined to st */
 	cudaStream_t sF = st, sT = st;
-	if (ctx->overlap && n_tiles > 1) {
+	if (ctx->overlap && n_tiles > 1 && fp0.ch == 0) {
 		sF = ctx->s_fir;
 		sT = ctx->s_trk;
 		CK(cudaStreamWaitEvent(sF, ctx->ev[EV_START], 0));
 		CK(cudaStreamWaitEvent(sT, ctx->ev[EV_START], 0));
 	}
 	for (int t = 0; t < n_tiles; t++) {
-		int64_t f0 = (int64_t) t * ctx->tile_frames;
-		int64_t nf = (n_frames - f0 < ctx->tile_frames) ? n_frames - f0 : ctx->tile_frames;
-		SampleView v;
-		v.ch_stride = planar ? stride : 1;
-		v.t_stride = planar ? 1 : stride;
+		int64_t f0 = (int64_t) t * tile;
+		int64_t nf = (n_frames - f0 < tile) ? n_frames - f0 : tile;
+		SampleView v = v0;
 		v.base = d_samples + f0 * v.t_stride;
 		if ((rc = enqueue_tile(ctx, v, nf, t, f0 / 32, sF, sT, true)) != 0)
 			return rc;
@@ -538,6 +652,17 @@ extern "C" int gais_run_host(gais_ctx *ctx, const int16_t *h_samples, int64_t n_
 	int n_tiles = (int) ((n_frames + tile - 1) / tile);
 	if ((rc = ensure_tile_events(ctx, n_tiles)) != 0)
 		return rc;
+	{
+		SampleView sv;
+		sv.base = ctx->d_stage[0];
+		sv.ch_stride = planar ? tile : 1;
+		sv.t_stride = planar ? 1 : stride;
+		const int64_t nf0 = n_frames < tile ? n_frames : tile, nfl = n_frames - (int64_t) (n_tiles - 1) * tile;
+		int64_t words = tile_sign_words(ctx, fused_part(ctx, sv, nf0), nf0);
+		const int64_t wl = tile_sign_words(ctx, fused_part(ctx, sv, nfl), nfl);
+		if ((rc = ensure_signs(ctx, wl > words ? wl : words)) != 0)
+			return rc;
+	}
 	CK(cudaEventRecord(ctx->ev[EV_START], st));
 	for (int t = 0; t < n_tiles; t++) {
 		int64_t f0 = (int64_t) t * tile;

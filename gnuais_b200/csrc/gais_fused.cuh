@@ -1,0 +1,583 @@
+/*
+ * gais_fused.cuh -- the whole per-sample chain of receiver_run() in ONE persistent kernel:
+ * int16 samples -> FIR sign (src/filter.c:106-143, src/filter.h:40-49) -> zero-crossing DPLL, slicer, NRZI
+ * (src/receiver.c:107-135) -> HDLC bit machine (src/protodec.c:988-1122) -> frame candidates.  The sign words
+ * never leave the SM: the FIR half hands them to the tracking half through a shared-memory ring.
+ *
+ * Why one kernel.  As two kernels (gais_fir_tc.cuh, gais_track.cuh) the FIR is bound by a chain of short
+ * waits (mbarrier round trips, tcgen05.ld, TMA latency; issue slots 60 % used) and the tracker by the serial
+ * per-channel dependency chains of 3.5 warps per scheduler (56 % used); each leaves about half of the issue
+ * slots idle, and they cannot share an SM (4 FIR CTAs take all 512 TMEM columns and 61 K registers), so a step
+ * costs the SUM of the two (profiles/r2_ncu_two_kernels.txt).  Here both halves are warps of the same CTA:
+ * one CTA per SM owns up to 15 channel sets (32 channels each = one tracker warp each) for the whole run, and
+ * the FIR half works through its 2 x sets channel groups round robin, one 256-sample stage at a time, so every
+ * tracker warp gets a new block of 8 sign words each round.
+ *
+ * Warps of a CTA (4 + 4 X_EPI + 16):
+ *   0, 1, 3 flip: bit 7 of every sample of a landed stage, in place (see gais_fir_tc.cuh), every third item each;
+ *           on a group's first stage they also drop the carried history into the zero-filled block
+ *   12      resolver: once per round, settles the outputs the integer contraction left open (tiers 2/3 of
+ *           gais_fir.cuh from global memory, ~2.6e-4 of noisy audio) and clears their provisional 1 bits
+ *   2       the three tcgen05.mma of every stage, by one elected lane (4 accumulator slots of 128 TMEM columns,
+ *           so the tensor core never waits for an epilogue)
+ *   4..11   epilogue: TMEM -> Q -> one sign word per thread (warp w: TMEM lane quadrant w % 4, the items of parity
+ *           (w - 4) / 4) -> sign ring [set][slot][channel][word]
+ *   13..27  trackers: one warp per channel set, one lane per channel: the loop of gais_track.cuh's
+ *           track_kernel, reading its sign words from the ring
+ *
+ * Flow control is all mbarriers (no CTA-wide barrier after the set-up):
+ *   in_full (TMA landed) -> in_flip (flipped) -> [issuer; also waits tmem_empty of the slot and
+ *   sign_empty of the set's ring slot] -> mma_done (tcgen05.commit) -> [epilogue; its first lane also sends the TMA
+ *   request that refills the input slot the MMAs have just finished with] -> tmem_empty, sign_pre (8 warp arrivals
+ *   per set and round) -> [resolver] -> sign_ready -> [tracker] -> sign_empty.
+ */
+#ifndef GAIS_FUSED_CUH
+#define GAIS_FUSED_CUH
+
+#include "gais_fir_tc.cuh"
+#include "gais_track.cuh"
+
+namespace gais {
+
+constexpr int X_SETS = 15;                       /* channel sets (32 channels) per CTA at most */
+#ifndef X_NS
+#define X_NS 8                                  /* input ring: stages of 9216 B */
+#endif
+constexpr int X_TS = 4;                          /* accumulator slots in TMEM (128 columns each) */
+constexpr int X_D = 4;                           /* sign ring: blocks of 8 words per channel set */
+constexpr int X_SIGN_ROW = 9;                    /* words per channel in a block: 8 + 1 (lanes 9 words apart: no bank conflicts) */
+constexpr int X_SIGN_BLOCK = 32 * X_SIGN_ROW * 4;
+constexpr int X_QCAP = 192;                      /* open outputs per round (expected ~2 per set) */
+#ifndef X_DIAG
+#define X_DIAG 0                                 /* diagnostics builds only (wrong results): 1 no flip work, 2 no epilogue arithmetic, 4 trackers only consume */
+#endif
+#ifndef X_SLEEP_EPI
+#define X_SLEEP_EPI 100                          /* ns between polls of a waiting epilogue / flip / tracker / resolver warp (0: bare try_wait loop) */
+#endif
+#ifndef X_SLEEP_FLIP
+#define X_SLEEP_FLIP 100
+#endif
+#ifndef X_SLEEP_TRK
+#define X_SLEEP_TRK 400
+#endif
+#ifndef X_EPI
+#define X_EPI 3                                  /* epilogue warps per TMEM lane quadrant: warp t takes the items k = t (mod X_EPI) */
+#endif
+constexpr int X_WARPS = 4 + 4 * X_EPI + 16, X_THREADS = X_WARPS * 32;
+constexpr int X_W_RES = 4 + 4 * X_EPI;           /* resolver warp; the trackers follow */
+constexpr int X_MAX_FRAMES = 1 << 22;            /* per launch: sample indices travel in 23 bits */
+
+constexpr int XO_BMAT = 0;
+constexpr int XO_RING = XO_BMAT + U_BMAT_BYTES;
+constexpr int XO_SIGN = XO_RING + X_NS * P_STAGE_BYTES;
+constexpr int XO_NTAB = XO_SIGN + X_SETS * X_D * X_SIGN_BLOCK;
+constexpr int XO_TAB = XO_NTAB + H_NSTATES * 16 * 4;
+constexpr int XO_Q = XO_TAB + H_NSTATES * 2 * 2;
+constexpr int XO_QN = XO_Q + X_D * X_QCAP * 4;
+constexpr int XO_BAR = (XO_QN + X_D * 4 + 7) / 8 * 8;
+/* barrier indices */
+constexpr int XB_IN_FULL = 0, XB_IN_FLIP = XB_IN_FULL + X_NS, XB_MMA = XB_IN_FLIP + X_NS,
+	      XB_TMEM_EMPTY = XB_MMA + X_TS, XB_SIGN_PRE = XB_TMEM_EMPTY + X_TS, XB_SIGN_READY = XB_SIGN_PRE + X_SETS * X_D,
+	      XB_SIGN_EMPTY = XB_SIGN_READY + X_SETS * X_D, XB_COUNT = XB_SIGN_EMPTY + X_SETS * X_D;
+constexpr int X_SMEM_BYTES = XO_BAR + XB_COUNT * 8 + 1024;      /* + alignment slack */
+static_assert(XO_RING % 512 == 0 && P_STAGE_BYTES % 512 == 0, "ring slots must keep the swizzle phase");
+static_assert(X_SMEM_BYTES <= 227 * 1024, "shared memory");
+static_assert(X_NS % 2 == 0, "ring slots: an even number (refills keep their item parity)");
+
+struct XArgs {
+	const int16_t *base;       /* sample (c, n) of the launch at base[c * ch_stride + n] */
+	int64_t ch_stride;
+	ChanState *st;
+	uint32_t *signs_out;       /* GAIS_KEEP_SIGNS: [word][n_channels], word 0 = first word of this launch; else NULL */
+	int hist_sel, n_channels, n_stages, sets_total, sets_per_cta, save_hist, kc;
+	int one, two16;            /* 1 and 65536, as values the compiler cannot fold (x_q) */
+	TrackOut out;
+};
+
+/* a wait that may be long, by a warp whose issue slots the other roles need: poll, and sleep between polls (a bare
+ * try_wait loop comes back every ~30 cycles: the waiting tracker warps of the first version took 27 % of all issue slots
+ * while the epilogue warps they were waiting for got their fair seventh, profiles/r2_fused_v1_summary.txt) */
+template <int NS_SLEEP>
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity)
+{
+	if (NS_SLEEP == 0) {
+		mbar_wait(bar, parity);
+		return;
+	}
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+		"@p bra D_%=;\n\t"
+		"W_%=:\n\t"
+		"nanosleep.u32 %2;\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+		"@!p bra W_%=;\n\t"
+		"D_%=:\n\t}" ::"r"(bar), "r"(parity), "n"(NS_SLEEP) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+
+/* 16 outputs from three accumulator slices (the arithmetic of gais_fir_umma.cuh umma_half_word): Q = D24 + floor((256 D16 +
+ * D8 + kc) / 65536), the floor and the add in one mad.hi.  neg: Q < 0; clr: Q == 0 and certainly negative; pend: open.
+ * The outputs are taken last first, so that the sign bits shift into place without a bit reversal; the rare Q == 0
+ * (1e-3 of noisy audio, i.e. in four of ten warps) is looked for in the group of four outputs it is in only. */
+#ifndef X_QMODE
+#define X_QMODE 0
+#endif
+/* The ALU pipe (IADD3 / LOP3 / SHF / LEA / VIMNMX: one warp instruction per 2 cycles and scheduler) is what this kernel
+ * runs out of first -- the tracking loop is nearly all ALU work -- while the FMA pipe (IMAD) is mostly idle; so the epilogue's
+ * adds and shifts are written as multiply-adds with multipliers the compiler cannot see through (one = 1, two16 = 65536,
+ * kernel arguments): p = d16 * 256 + d8 (IMAD), p += kc (IMAD), Q = d24 + hi32(p * 65536) (IMAD.HI) */
+__device__ __forceinline__ int x_q(uint32_t d24, uint32_t d16, uint32_t d8, int kc, int one, int two16, int &p)
+{
+	int q;
+#if X_QMODE == 0
+	p = (int) d16 * 256 + ((int) d8 + kc);
+	asm("mad.hi.s32 %0, %1, 65536, %2;" : "=r"(q) : "r"(p), "r"((int) d24));
+#elif X_QMODE == 1
+	int t;
+	asm("mad.lo.s32 %0, %1, 256, %2;" : "=r"(t) : "r"((int) d16), "r"((int) d8));
+	asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(p) : "r"(t), "r"(one), "r"(kc));
+	asm("mad.hi.s32 %0, %1, 65536, %2;" : "=r"(q) : "r"(p), "r"((int) d24));
+#else
+	int t;
+	asm("mad.lo.s32 %0, %1, 256, %2;" : "=r"(t) : "r"((int) d16), "r"((int) d8));
+	asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(p) : "r"(t), "r"(one), "r"(kc));
+	asm("mad.hi.s32 %0, %1, %2, %3;" : "=r"(q) : "r"(p), "r"(two16), "r"((int) d24));
+#endif
+	return q;
+}
+__device__ __forceinline__ void x_half_word(const uint32_t (&d24)[16], const uint32_t (&d16)[16], const uint32_t (&d8)[16], int kc, int one,
+					    int two16, uint32_t &neg, uint32_t &clr, uint32_t &pend)
+{
+	uint32_t sg[2] = { 0, 0 }, mn[4];
+#pragma unroll
+	for (int c = 3; c >= 0; c--) {
+		mn[c] = 0xffffffffu;
+#pragma unroll
+		for (int j = 4 * c + 3; j >= 4 * c; j--) {
+			int p;
+			const int q = x_q(d24[j], d16[j], d8[j], kc, one, two16, p);
+			sg[c >> 1] = __funnelshift_l((uint32_t) q, sg[c >> 1], 1);     /* two chains of 8: bit i of sg[b] = sign of output 8 b + i */
+			mn[c] = min(mn[c], (uint32_t) q);
+		}
+	}
+	neg = sg[0] | (sg[1] << 8);
+	pend = 0;
+	clr = 0;
+	if (min(min(mn[0], mn[1]), min(mn[2], mn[3])) == 0u) {
+#pragma unroll
+		for (int c = 0; c < 4; c++)
+			if (mn[c] == 0u) {
+#pragma unroll
+				for (int j = 4 * c; j < 4 * c + 4; j++) {
+					int p;
+					if (x_q(d24[j], d16[j], d8[j], kc, one, two16, p) == 0) {
+						const int v = (p & 0xffff) - 32768;
+						if (v <= -U_VGUARD)
+							clr |= 1u << j;
+						else if (v < U_VGUARD)
+							pend |= 1u << j;
+					}
+				}
+			}
+	}
+}
+
+/* the open outputs of one half word go to the round's queue (the provisional bit 1 stays in the sign word);
+ * with the queue full they are settled on the spot.  Returns the bits to clear */
+__device__ __noinline__ uint32_t x_push(uint32_t pend, uint32_t item0, uint32_t qn_a, uint32_t q_a, const int16_t *__restrict__ row,
+					const int16_t *__restrict__ hist)
+{
+	uint32_t clr = 0;
+	while (pend) {
+		const uint32_t j = (uint32_t) __ffs((int) pend) - 1u;
+		pend &= pend - 1u;
+		uint32_t pos;
+		asm volatile("atom.shared::cta.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(qn_a) : "memory");
+		if (pos < (uint32_t) X_QCAP)
+			asm volatile("st.shared.u32 [%0], %1;" ::"r"(q_a + 4u * pos), "r"(item0 + j) : "memory");
+		else if (umma_resolve_global(row, hist, (int) ((item0 + j) & 0x7fffffu)) == 0u)
+			clr |= 1u << j;
+	}
+	return clr;
+}
+
+/* ---- tracker warp: gais_track.cuh's track_kernel with the sign words coming from the ring ---- */
+__device__ __forceinline__ void x_track_role(const XArgs &a, int c, uint32_t ring_a /* this set's X_D blocks */, uint32_t ready_a,
+					     uint32_t empty_a, const uint32_t *ntab, const uint16_t *tab)
+{
+	const uint32_t lane = threadIdx.x & 31u, wmask = 0xffffffffu;
+	ChanState *s = &a.st[c];
+	const TrackOut &out = a.out;
+	uint32_t prevword = (uint32_t) s->prev << 31;
+	uint32_t dlo = s->dacc, nd = s->nd;
+	uint32_t hb = s->n_bits - nd;
+	uint32_t zb = (nd << 16) | (s->pll & 0xffffu);
+	HdlcRegs f;
+	f.id = s->fsm; f.pos = s->pos; f.shi = s->cur; f.slo = s->cur2;
+	uint32_t ncand = out.run_count[c], nsize = 0;
+	const uint32_t bits_start = hb + nd;
+	const uint32_t run_start = bits_start - out.run_bits[c];
+
+	const uint32_t my_row = ring_a + lane * (X_SIGN_ROW * 4);
+	for (int blk = 0; blk < a.n_stages; blk++) {
+		const uint32_t slot = (uint32_t) blk % X_D;
+		mbar_wait_sleep<X_SLEEP_TRK>(ready_a + 8u * slot, ((uint32_t) blk / X_D) & 1u);
+		const uint32_t src = my_row + slot * X_SIGN_BLOCK;
+		uint32_t nxt = lds32(src);
+		if (X_DIAG & 4)
+			prevword ^= nxt;
+		else
+#pragma unroll 1
+		for (uint32_t w = 0; w < 8u; w++) {
+			const uint32_t sw = nxt;
+			if (w < 7u)
+				nxt = lds32(src + 4u * w + 4u);
+			const uint32_t x = sw ^ __funnelshift_l(prevword, sw, 1);
+			prevword = sw;
+			dpll_word(x, zb, dlo);
+			zb += 32u * GAIS_PLL_INC;
+			nd = zb >> 16;
+			if (__any_sync(wmask, nd >= 24u)) {
+				const uint32_t W = ~dlo;
+				if (out.bits && nd >= 4u)
+					bits_or(out, c, (int64_t) (int32_t) (hb - run_start), W, nd & ~3u);
+				const uint32_t used = hdlc_chunk(f, tab, ntab, W, nd, hb, false, s, c, ncand, nsize, out, wmask);
+				dlo >>= used;
+				hb += used;
+				nd -= used;
+				zb -= used << 16;
+			}
+		}
+		__syncwarp();
+		if (lane == 0u)
+			mbar_arrive(empty_a + 8u * slot);
+	}
+	if (__any_sync(wmask, nd != 0u)) {
+		/* end of the launch: hand all sliced bits over (same as the end of a tile in track_kernel) */
+		const uint32_t W = ~dlo;
+		if (out.bits && nd)
+			bits_or(out, c, (int64_t) (int32_t) (hb - run_start), W, nd);
+		hdlc_chunk(f, tab, ntab, W, nd, hb, true, s, c, ncand, nsize, out, wmask);
+		dlo >>= nd;
+		hb += nd;
+		zb -= nd << 16;
+		nd = 0;
+	}
+	s->pll = zb & 0xffffu; s->n_bits = hb + (zb >> 16); s->prev = (uint8_t) (prevword >> 31);
+	s->dacc = dlo; s->nd = (uint8_t) nd;
+	s->lastbit = (uint8_t) (((prevword >> 31) ^ (dlo >> nd)) & 1u);
+	s->fsm = (uint8_t) f.id; s->pos = (uint16_t) f.pos; s->cur = f.shi; s->cur2 = f.slo;
+	out.run_count[c] = ncand;
+	s->sizefail += (int32_t) nsize;
+	out.run_bits[c] += hb + (zb >> 16) - bits_start;
+	if (a.save_hist) {
+		/* the launch ends the tile: its last 36 samples are the next one's history (src/filter.c:129-134) */
+		const int16_t *row = a.base + (int64_t) c * a.ch_stride + (int64_t) a.n_stages * P_T - GAIS_NTAPS;
+#pragma unroll 4
+		for (int i = 0; i < GAIS_NTAPS; i++)
+			s->hist[a.hist_sel ^ 1][i] = row[i];
+	}
+}
+
+/* TMA request for item j = (group g, stage s) of the CTA into ring slot j % X_NS: 16 channel rows x (32 + 256) samples */
+__device__ __forceinline__ void x_load(const CUtensorMap &tmap, uint32_t bar_a, uint32_t ring_a, int set0, int j, int g, int s)
+{
+	const uint32_t slot = (uint32_t) j % X_NS;
+	mbar_expect_tx(bar_a + 8 * (XB_IN_FULL + slot), (uint32_t) P_STAGE_BYTES);
+	tma_g2s_3d(ring_a + slot * P_STAGE_BYTES, &tmap, 0, 8 * s - 1, (set0 + (g >> 1)) * 32 + (g & 1) * 16, bar_a + 8 * (XB_IN_FULL + slot));
+}
+
+__global__ void __launch_bounds__(X_THREADS, 1)
+ais_fused_kernel(const __grid_constant__ CUtensorMap tmap, const XArgs a)
+{
+	extern __shared__ __align__(1024) uint8_t x_smem_raw[];
+	__shared__ uint32_t tmem_base_s;
+
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const uint32_t raw_a = smem_u32(x_smem_raw);
+	const uint32_t smem0 = (raw_a + 1023u) & ~1023u;
+	uint8_t *const smem_g = x_smem_raw + (smem0 - raw_a);
+	const uint32_t bmat_a = smem0 + XO_BMAT, ring_a = smem0 + XO_RING, sign_a = smem0 + XO_SIGN, q_a = smem0 + XO_Q, qn_a = smem0 + XO_QN,
+		       bar_a = smem0 + XO_BAR;
+	uint32_t *const ntab = reinterpret_cast<uint32_t *>(smem_g + XO_NTAB);
+	uint16_t *const tab = reinterpret_cast<uint16_t *>(smem_g + XO_TAB);
+
+	const int set0 = blockIdx.x * a.sets_per_cta;
+	const int n_sets = min(a.sets_per_cta, a.sets_total - set0);
+	const int G = 2 * n_sets;                    /* channel groups of 16 */
+	const int K = a.n_stages * G;                /* (group, stage) items, in round-robin order: k = s * G + g */
+
+	/* ---- set-up ---- */
+	if (tid == 0) {
+		for (int i = 0; i < X_NS; i++) {
+			mbar_init(bar_a + 8 * (XB_IN_FULL + i), 1);
+			mbar_init(bar_a + 8 * (XB_IN_FLIP + i), 1);
+		}
+		for (int i = 0; i < X_TS; i++) {
+			mbar_init(bar_a + 8 * (XB_MMA + i), 1);
+			mbar_init(bar_a + 8 * (XB_TMEM_EMPTY + i), 4);
+		}
+		for (int i = 0; i < X_SETS * X_D; i++) {
+			mbar_init(bar_a + 8 * (XB_SIGN_PRE + i), 8);      /* 2 groups x 4 quadrant warps */
+			mbar_init(bar_a + 8 * (XB_SIGN_READY + i), 1);
+			mbar_init(bar_a + 8 * (XB_SIGN_EMPTY + i), 1);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		for (int i = 0; i < X_D; i++)
+			reinterpret_cast<uint32_t *>(smem_g + XO_QN)[i] = 0;
+	}
+	for (int i = tid; i < U_BMAT_BYTES / 16; i += X_THREADS) {
+		const uint4 v = reinterpret_cast<const uint4 *>(g_umma_bmat)[i];
+		asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(bmat_a + 16 * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+	}
+	for (int i = tid; i < H_NSTATES * 16; i += X_THREADS)
+		ntab[i] = hdlc_nibble_entry((uint32_t) i >> 4, (uint32_t) i & 15u);
+	for (int i = tid; i < H_NSTATES * 2; i += X_THREADS)
+		tab[i] = (uint16_t) hdlc_transition((uint32_t) i >> 1, (uint32_t) i & 1u);
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	if (warp == 0) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+	const uint32_t tmem = tmem_base_s;
+
+	if (warp == 2) {
+		/* ===== MMA issue.  The whole warp walks the loop (uniform control flow: the waits and counters compile to a few
+		 * instructions; as one divergent lane the loop was 120 instructions of ELECT / R2UR / BRA.U.ANY per item and,
+		 * sharing its scheduler with six other warps, THE bottleneck of the first version at 1250 cycles per item,
+		 * profiles/r2_fused_experiments.txt); one elected lane issues the tcgen05 instructions ===== */
+		uint32_t elected;
+		asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+		if (elected) {
+			/* the first X_NS items; after that the epilogue refills a ring slot as soon as it has seen the slot's MMAs complete */
+			int jg = 0, js = 0;
+			for (int j = 0; j < X_NS && j < K; j++) {
+				x_load(tmap, bar_a, ring_a, set0, j, jg, js);
+				if (++jg == G) { jg = 0; js++; }
+			}
+		}
+		__syncwarp();
+		int g = 0, s = 0;
+		uint32_t islot = 0, in_par = 0, tslot = 0, t_par = 1, sslot = 0, s_par = 1;     /* ring positions and the parities to wait for */
+		for (int k = 0; k < K; k++) {
+			mbar_wait(bar_a + 8 * (XB_IN_FLIP + islot), in_par);
+			if (k >= X_TS)
+				mbar_wait(bar_a + 8 * (XB_TMEM_EMPTY + tslot), t_par);
+			if (s >= X_D && !(g & 1))        /* the tracker of this set has read the block that this stage's signs will overwrite */
+				mbar_wait(bar_a + 8 * (XB_SIGN_EMPTY + (g >> 1) * X_D + sslot), s_par);
+			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+			if (elected) {
+				const uint32_t a0 = ring_a + islot * P_STAGE_BYTES + 16u;
+#pragma unroll
+				for (int kk = 0; kk < 3; kk++) {
+					const uint64_t ad = P_ADESC | (uint64_t) (((a0 + 32u * kk) & 0x3FFFFu) >> 4);
+					const uint64_t bd = U_BDESC | (uint64_t) (((bmat_a + (uint32_t) (kk * U_BK_BYTES)) & 0x3FFFFu) >> 4);
+					asm volatile(
+						"{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+						"tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+						::"r"(tmem + tslot * 128u), "l"(ad), "l"(bd), "r"(U_IDESC), "r"(kk ? 1u : 0u), "r"(0u) : "memory");
+				}
+				asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_a + 8 * (XB_MMA + tslot)) : "memory");
+			}
+			__syncwarp();
+			if (++islot == X_NS) { islot = 0; in_par ^= 1u; }
+			if (++tslot == X_TS) { tslot = 0; t_par ^= 1u; }
+			if (++g == G) {
+				g = 0;
+				s++;
+				if (++sslot == X_D) { sslot = 0; s_par ^= 1u; }
+			}
+		}
+	} else if (warp < 4) {
+		/* ===== flip: warps 0, 1, 3 take every third item each, a whole stage at a time (18 chunks of 16 B per lane).
+		 * Two warps sharing every item were the bottleneck of the bare pipeline: with the flip work compiled out it ran at
+		 * 406 instead of 707 cycles per item (profiles/r2_fused_experiments.txt) -- an item's flip is one long chain
+		 * (wait, LDS, XOR, STS, proxy fence, arrive), so what helps is more items in flight, not more lanes per item ===== */
+		const int fw = warp == 3 ? 2 : warp;
+		for (int k = fw; k < K; k += 3) {
+			const uint32_t slot = (uint32_t) k % X_NS, slot_a = ring_a + slot * P_STAGE_BYTES;
+			mbar_wait_sleep<X_SLEEP_FLIP>(bar_a + 8 * (XB_IN_FULL + slot), (uint32_t) (k / X_NS) & 1u);
+			if (X_DIAG & 1) {
+			} else if (k < G) {
+				/* a group's first stage: TMA zero-filled the block before the launch's first sample; samples -32..-1 are
+				 * hist[4..35] (src/filter.c:129-134).  swz64 is an involution on the slot offset: chunk p holds the
+				 * row bytes at offset swz64(16 p) */
+				const int ch0 = (set0 + (k >> 1)) * 32 + (k & 1) * 16;
+#pragma unroll 6
+				for (int i = 0; i < P_STAGE_CHUNKS / 32; i++) {
+					const uint32_t off = 16u * (32u * i + lane), lin = swz64(off);
+					const uint32_t row = lin / P_ROW_BYTES, col = lin % P_ROW_BYTES;
+					uint4 v;
+					if (col < 64u) {
+						const uint32_t *h = reinterpret_cast<const uint32_t *>(a.st[ch0 + row].hist[a.hist_sel] + 4 + (col >> 1));
+						v = make_uint4(h[0], h[1], h[2], h[3]);
+					} else
+						v = lds128(slot_a + off);
+					asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot_a + off), "r"(v.x ^ 0x00800080u),
+						     "r"(v.y ^ 0x00800080u), "r"(v.z ^ 0x00800080u), "r"(v.w ^ 0x00800080u)
+						     : "memory");
+				}
+			} else {
+#pragma unroll
+				for (int b = 0; b < 2; b++) {
+					uint4 v[9];
+#pragma unroll
+					for (int i = 0; i < 9; i++)
+						v[i] = lds128(slot_a + 16u * (32u * (9 * b + i) + lane));
+#pragma unroll
+					for (int i = 0; i < 9; i++)
+						asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot_a + 16u * (32u * (9 * b + i) + lane)),
+							     "r"(v[i].x ^ 0x00800080u), "r"(v[i].y ^ 0x00800080u), "r"(v[i].z ^ 0x00800080u), "r"(v[i].w ^ 0x00800080u)
+							     : "memory");
+				}
+			}
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(bar_a + 8 * (XB_IN_FLIP + slot));
+		}
+	} else if (warp == X_W_RES) {
+		/* ===== resolver ===== */
+		for (int s = 0; s < a.n_stages; s++) {
+			const uint32_t slot = (uint32_t) s % X_D, par = ((uint32_t) s / X_D) & 1u;
+			if (lane < n_sets)
+				mbar_wait_sleep<X_SLEEP_TRK>(bar_a + 8 * (XB_SIGN_PRE + lane * X_D + slot), par);
+			__syncwarp();
+			const uint32_t nq = min(lds32(qn_a + 4u * slot), (uint32_t) X_QCAP);
+			for (uint32_t e = lane; e < nq; e += 32u) {
+				const uint32_t item = lds32(q_a + 4u * (slot * X_QCAP + e));
+				const int set_l = (int) (item >> 28), chl = (int) ((item >> 23) & 31u), n = (int) (item & 0x7fffffu);
+				const int ch = (set0 + set_l) * 32 + chl;
+				if (umma_resolve_global(a.base + (int64_t) ch * a.ch_stride, a.st[ch].hist[a.hist_sel], n) == 0u) {
+					const uint32_t mask = ~(1u << (n & 31));
+					atomicAnd(reinterpret_cast<uint32_t *>(smem_g + XO_SIGN + ((set_l * X_D + (int) slot) * 32 + chl) * (X_SIGN_ROW * 4) +
+									       ((n >> 5) & 7) * 4), mask);
+					if (a.signs_out)
+						atomicAnd(a.signs_out + (int64_t) (n >> 5) * a.n_channels + ch, mask);
+				}
+			}
+			__syncwarp();
+			if (lane == 0 && nq)
+				asm volatile("st.shared.u32 [%0], %1;" ::"r"(qn_a + 4u * slot), "r"(0u) : "memory");
+			__syncwarp();
+			if (lane < n_sets)
+				mbar_arrive(bar_a + 8 * (XB_SIGN_READY + lane * X_D + slot));
+		}
+	} else if (warp >= 4 && warp < X_W_RES) {
+		/* ===== epilogue: warp = (TMEM lane quadrant, item parity); both half words of every other item ===== */
+		const int qd = warp & 3, par = (warp - 4) >> 2;
+		const int m = 32 * qd + lane, c16 = m >> 3, r = m & 7;         /* MMA row: channel c16 of the group, word r of the stage */
+		const uint32_t taddr0 = tmem + ((uint32_t) (32 * qd) << 16);
+		const uint32_t my_sign = sign_a + (uint32_t) c16 * (X_SIGN_ROW * 4) + (uint32_t) r * 4;
+		const int ref_dg = X_NS % G, ref_ds = X_NS / G;
+		int g = par % G, s = par / G;
+		for (int k = par; k < K; k += X_EPI) {
+			const uint32_t tslot = (uint32_t) k % X_TS;
+			mbar_wait_sleep<X_SLEEP_EPI>(bar_a + 8 * (XB_MMA + tslot), (uint32_t) (k / X_TS) & 1u);
+			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+			if (qd == 0 && lane == 0 && k + X_NS < K) {
+				/* the MMAs of item k are complete, so its ring slot is free: request item k + X_NS (same parity, X_NS is even) */
+				int g2 = g + ref_dg, s2 = s + ref_ds;
+				if (g2 >= G) { g2 -= G; s2++; }
+				x_load(tmap, bar_a, ring_a, set0, k + X_NS, g2, s2);
+			}
+			const uint32_t taddr = taddr0 + tslot * 128u;
+			const int set_l = g >> 1, chl = (g & 1) * 16 + c16;
+			const uint32_t slot = (uint32_t) s % X_D;
+			uint32_t word = 0;
+#pragma unroll
+			for (int h = 0; h < 2; h++) {
+				uint32_t d24[16], d16[16], d8[16], neg, clr, pend;
+				tmem_ld16(taddr + 16 * h, d24);
+				tmem_ld16(taddr + 32 + 16 * h, d16);
+				tmem_ld16(taddr + 64 + 16 * h, d8);
+				asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+				if (h == 1) {
+					/* the accumulators are in registers: the slot may take the MMAs of item k + 4 */
+					asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+					__syncwarp();
+					if (lane == 0)
+						mbar_arrive(bar_a + 8 * (XB_TMEM_EMPTY + tslot));
+				}
+				if (X_DIAG & 2) {
+					neg = d24[0] ^ d16[3] ^ d8[7]; clr = 0; pend = 0;
+				} else
+					x_half_word(d24, d16, d8, a.kc, a.one, a.two16, neg, clr, pend);
+				if (pend) {
+					const int ch = (set0 + set_l) * 32 + chl;
+					clr |= x_push(pend, ((uint32_t) set_l << 28) | ((uint32_t) chl << 23) | (uint32_t) (s * P_T + 32 * r + 16 * h),
+						      qn_a + 4u * slot, q_a + 4u * slot * X_QCAP, a.base + (int64_t) ch * a.ch_stride,
+						      a.st[ch].hist[a.hist_sel]);
+				}
+				word |= (~(neg | clr) & 0xffffu) << (16 * h);          /* bit j = (filtered[32 w + j] > 0) */
+			}
+			asm volatile("st.shared.u32 [%0], %1;" ::"r"(my_sign + (uint32_t) ((set_l * X_D + (int) slot) * 32 + (g & 1) * 16) * (X_SIGN_ROW * 4)), "r"(word) : "memory");
+			if (a.signs_out)
+				a.signs_out[((int64_t) s * (P_T / 32) + r) * a.n_channels + (set0 + set_l) * 32 + chl] = word;
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(bar_a + 8 * (XB_SIGN_PRE + set_l * X_D + slot));
+			g += X_EPI;
+			while (g >= G) { g -= G; s++; }
+		}
+	} else if (warp > X_W_RES) {
+		/* ===== trackers: warps 13..27 <-> sets 0..14 (14 sets per CTA at 65536 channels on 148 SMs: warp 27 idle) ===== */
+		const int set_l = warp - X_W_RES - 1;
+		if (set_l < n_sets)
+			x_track_role(a, (set0 + set_l) * 32 + lane, sign_a + set_l * X_D * X_SIGN_BLOCK, bar_a + 8 * (XB_SIGN_READY + set_l * X_D),
+				     bar_a + 8 * (XB_SIGN_EMPTY + set_l * X_D), ntab, tab);
+	}
+
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	if (warp == 0)
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+
+static inline int fused_setup(void)
+{
+	return cudaFuncSetAttribute(ais_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, X_SMEM_BYTES) == cudaSuccess ? 0 : -1;
+}
+
+/* channels [0, n_fused_ch) x samples [0, n_fused_frames) of the view: n_fused_ch % 32 == 0, n_fused_frames % 256 == 0 and
+ * <= X_MAX_FRAMES; planar, 16-byte aligned rows.  Returns the number of launches (1), < 0 on error */
+static inline int fused_launch(SampleView view, ChanState *st, int hist_sel, int n_ch, int n_fused_ch, int64_t n_fused_frames, int save_hist,
+			       uint32_t *signs_out, const TrackOut &out, int n_sms, cudaStream_t stream)
+{
+	CUtensorMap tm;
+	if (!fir_tc_make_tmap(&tm, view.base, view.ch_stride, n_fused_ch, n_fused_frames))
+		return -1;
+	XArgs a;
+	a.base = view.base;
+	a.ch_stride = view.ch_stride;
+	a.st = st;
+	a.signs_out = signs_out;
+	a.hist_sel = hist_sel;
+	a.n_channels = n_ch;
+	a.n_stages = (int) (n_fused_frames / P_T);
+	a.sets_total = n_fused_ch / 32;
+	int spc = (a.sets_total + n_sms - 1) / n_sms;
+	if (spc > X_SETS)
+		spc = X_SETS;
+	a.sets_per_cta = spc;
+	a.save_hist = save_hist;
+	a.kc = g_umma_kc;
+	a.one = 1;
+	a.two16 = 65536;
+	a.out = out;
+	const unsigned grid = (unsigned) ((a.sets_total + spc - 1) / spc);
+	ais_fused_kernel<<<grid, X_THREADS, X_SMEM_BYTES, stream>>>(tm, a);
+	return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+} /* namespace gais */
+#endif

@@ -357,8 +357,9 @@ __device__ __forceinline__ void dpll_word(uint32_t x, uint32_t &zb, uint32_t &dl
 }
 
 __global__ void __launch_bounds__(TRK_THREADS, TRK_MIN_BLOCKS)
-track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, int64_t n_frames, TrackOut out)
+track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int c_begin, int c_end, int n_channels, int64_t n_frames, TrackOut out)
 {
+	/* channels [c_begin, c_end) of a batch of n_channels (= the row length of the sign words) */
 	__shared__ uint32_t ntab[H_NSTATES * 16];
 	__shared__ uint16_t tab[H_NSTATES * 2];
 	for (int i = threadIdx.x; i < H_NSTATES * 16; i += TRK_THREADS)
@@ -367,8 +368,8 @@ track_kernel(const uint32_t *__restrict__ signs, ChanState *st, int n_channels, 
 		tab[i] = (uint16_t) hdlc_transition((uint32_t) i >> 1, (uint32_t) i & 1u);
 	__syncthreads();
 
-	const int c = blockIdx.x * blockDim.x + threadIdx.x;
-	if (c >= n_channels)
+	const int c = c_begin + blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= c_end)
 		return;
 	ChanState *s = &st[c];
 	/* the lanes that are left walk the same number of words and take the HDLC hand-over together: every vote in
@@ -578,10 +579,10 @@ frame_check_kernel(gais_msg *__restrict__ slots, uint32_t *__restrict__ run_coun
 	}
 }
 
-static inline int track_launch(const uint32_t *signs, ChanState *st, int n_ch, int64_t n_frames, const TrackOut &out,
+static inline int track_launch(const uint32_t *signs, ChanState *st, int c_begin, int c_end, int n_ch, int64_t n_frames, const TrackOut &out,
 			       cudaStream_t stream)
 {
-	track_kernel<<<(n_ch + TRK_THREADS - 1) / TRK_THREADS, TRK_THREADS, 0, stream>>>(signs, st, n_ch, n_frames, out);
+	track_kernel<<<(c_end - c_begin + TRK_THREADS - 1) / TRK_THREADS, TRK_THREADS, 0, stream>>>(signs, st, c_begin, c_end, n_ch, n_frames, out);
 	return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

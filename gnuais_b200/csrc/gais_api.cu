@@ -95,7 +95,7 @@ struct gais_ctx {
 	cudaStream_t s_copy, s_own, s_fir, s_trk;
 	cudaEvent_t ev_fir_done[2], ev_trk_done[2], ev_join;
 	int overlap;                /* GAIS_OVERLAP=1: FIR of tile t+1 concurrent with tracking of tile t (two-kernel path only) */
-	int fused;                  /* GAIS_FUSED=1 (default): the one-kernel chain of gais_fused.cuh wherever the input allows it */
+	int fused;                  /* 0: two kernels; 1 (default): the one-kernel chain of gais_fused.cuh for batches that fill the GPU; 2: wherever the input allows it */
 	int n_sms;
 	cudaEvent_t ev[EV_COUNT], ev_copy[2], ev_free[2];
 	cudaEvent_t *ev_tile;       /* 4 per tile: fir start, fir end, track start, track end */
@@ -278,7 +278,11 @@ extern "C" int gais_create(const gais_config *cfg, gais_ctx **out)
 
 	{
 		int64_t run_frames = cfg->max_frames_per_run;
-		ctx->fused = (int) env_i64("GAIS_FUSED", 1) && fir_impl() == 2;
+		/* which chain: reserved[4] 1 = the two kernels, 2 = the fused kernel wherever the input allows it, 0 = GAIS_FUSED
+		 * (same values; default 1... "auto": fused when the batch gives every SM at least two channel sets) */
+		ctx->fused = cfg->reserved[4] == 1 ? 0 : cfg->reserved[4] == 2 ? 2 : (int) env_i64("GAIS_FUSED", 1);
+		if (fir_impl() != 2)
+			ctx->fused = 0;
 		ctx->n_sms = prop.multiProcessorCount;
 		if (cfg->flags & GAIS_KEEP_SIGNS) {
 			ctx->sign_words = ((run_frames + tile - 1) / tile) * (tile / 32);
@@ -389,7 +393,11 @@ static FusedPart fused_part(const gais_ctx *ctx, const SampleView &view, int64_t
 	FusedPart p = { 0, 0 };
 	const bool aligned = ctx->cfg.layout == GAIS_LAYOUT_PLANAR && view.t_stride == 1 && (view.ch_stride % 8) == 0 &&
 			     ((uintptr_t) view.base % 16) == 0;
-	if (ctx->fused && ctx->cfg.fir_mode == GAIS_FIR_GUARD && aligned && n_frames <= X_MAX_FRAMES) {
+	/* small batches stay on the two kernels: below two channel sets per SM the chain is paced by one tracker warp walking
+	 * its block alone either way, and the stand-alone tracker (79 registers, no ring hand-over) walks it faster
+	 * (1024 channels x 480000: 10.4 vs 13.0 ms, profiles/r2_fused_experiments.txt) */
+	const bool want = ctx->fused == 2 || (ctx->fused == 1 && ctx->n_ch / 32 >= 2 * ctx->n_sms);
+	if (want && ctx->cfg.fir_mode == GAIS_FIR_GUARD && aligned && n_frames <= X_MAX_FRAMES) {
 		p.ch = ctx->n_ch / 32 * 32;
 		p.frames = n_frames / P_T * P_T;
 		if (p.ch == 0 || p.frames == 0)
@@ -432,7 +440,7 @@ static int ensure_signs(gais_ctx *ctx, int64_t words)
 /* enqueue the chain for one time tile whose samples are at `view` (n = 0 is the first sample of the tile).
  * The fused kernel (gais_fused.cuh) takes whole channel sets and whole 256-sample stages of aligned planar
  * input; the FIR-sign and tracking kernels sweep up what is left (ragged end of the tile, channels beyond a
- * multiple of 32) and everything else (interleaved or unaligned input, GAIS_FIR_EXACT, GAIS_FUSED=0). */
+ * multiple of 32) and everything else (interleaved or unaligned input, GAIS_FIR_EXACT, small batches, GAIS_FUSED=0). */
 static int enqueue_tile(gais_ctx *ctx, SampleView view, int64_t n_frames, int tile_idx, int64_t word_ofs, cudaStream_t st,
 			cudaStream_t st_trk, bool timed)
 {

@@ -37,7 +37,8 @@ class BatchReceiver:
 
     def __init__(self, n_channels: int, max_frames_per_run: int, layout: str = "planar", device: int = 0,
                  fir_mode: str = "guard", keep_bits: bool = False, keep_signs: bool = False,
-                 slot_cap: int = 0, tile_frames: int = 0, overlap=None, keep_peak: bool = False, first_channel: int = 0):
+                 slot_cap: int = 0, tile_frames: int = 0, overlap=None, keep_peak: bool = False, first_channel: int = 0,
+                 chain=None):
         self._lib = L.load()
         self._ctx = C.c_void_p()
         cfg = L.Config()
@@ -52,6 +53,8 @@ class BatchReceiver:
         cfg.reserved[1] = tile_frames
         cfg.reserved[2] = 0 if overlap is None else (2 if overlap else 1)
         cfg.reserved[3] = first_channel
+        # kernel chain: None = library default (fused kernel for batches that fill the GPU), "fused" / "two_kernel" force one
+        cfg.reserved[4] = {None: 0, "two_kernel": 1, "fused": 2}[chain]
         L.check(self._lib.gais_create(C.byref(cfg), C.byref(self._ctx)))
         self.n_channels = n_channels
         self.first_channel = first_channel

@@ -82,7 +82,11 @@ typedef struct gais_config {
 	                               [0] message slots per channel per run, [1] time-tile length in frames,
 	                               [2] FIR/tracking overlap across tiles (1 = off, 2 = on),
 	                               [3] number of this context's channel 0 in a batch sharded over several contexts /
-	                                   GPUs: gais_msg.channel = reserved[3] + local index; [4..7] must be 0 */
+	                                   GPUs: gais_msg.channel = reserved[3] + local index;
+	                               [4] kernel chain: 1 = FIR-sign kernel + tracking kernel, 2 = the fused kernel wherever the
+	                                   input allows it (planar, 16-byte aligned rows, GAIS_FIR_GUARD), 0 = the fused kernel
+	                                   for batches of at least two 32-channel sets per SM (or what GAIS_FUSED says);
+	                               [5..7] must be 0 */
 } gais_config;
 
 /* One CRC-ok HDLC frame, 64 bytes.  payload[j] is byte j of the frame as the reference packs

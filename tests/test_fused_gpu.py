@@ -4,7 +4,7 @@ in seconds (by default the library keeps small batches on the two-kernel path): 
 (reference: src/receiver.c:87-148, src/protodec.c:988-1122) and against the two-kernel path.  Shapes are chosen to
 hit the seams: channels beyond a multiple of 32 and samples beyond a multiple of 256 (swept up by the FIR-sign and
 tracking kernels), several runs on one context (carried history, DPLL phase, half-received frames), host buffers
-(one launch per staging tile), more channel sets than fit one CTA per SM (several waves)."""
+(one launch per staging tile), more channel sets than one wave of CTAs can own."""
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -93,10 +93,11 @@ def test_fused_chain_streams_and_host_buffers():
 
 
 def test_fused_chain_equals_two_kernel_chain_many_sets():
-    """20000 channels = 625 sets: more than one CTA per SM can own (15), so the grid runs in waves; 16 leftover
-    channels; records, counters and state equal the two-kernel chain's, a sample of channels equals the oracle"""
+    """71088 channels = 2221 sets + 16 leftover channels: more sets than one CTA per SM can own (15 x 148 = 2220), so the
+    grid does not fit one wave; records, counters and state equal the two-kernel chain's, a sample of channels equals
+    the oracle"""
     torch = torch_dev()
-    n_ch, n = 20016, 12800
+    n_ch, n = 2221 * 32 + 16, 6400
     p = SynthParams(seed=404, sigma=300.0, rho=0.6)
     d = torch.empty((n_ch, n), dtype=torch.int16, device="cuda")
     synth_device(p, d, n_ch, n)
@@ -109,7 +110,7 @@ def test_fused_chain_equals_two_kernel_chain_many_sets():
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
     assert len(a[0]) > 1000
     host = d.cpu().numpy()
-    for c in (0, 31, 32, 479, 480, 9999, 19999, 20000, 20015):
+    for c in (0, 31, 32, 479, 480, 9999, 40000, 71039, 71040, 71071, 71072, 71087):
         w = O.port().run(host[c], want_bits=False)
         cnt, st = a[1][c], a[2][c]
         assert (int(cnt["ok"]), int(cnt["crcfail"]), int(cnt["sizefail"])) == w.counters()

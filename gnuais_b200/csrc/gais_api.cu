@@ -91,6 +91,8 @@ struct gais_ctx {
 	int32_t *d_overflow;
 	unsigned long long *d_totals;
 	int16_t *d_stage[2];        /* gais_run_host staging tiles */
+	int16_t *d_planar;          /* planar copy of an interleaved tile (batches of >= 32 interleaved channels) */
+	int64_t planar_elems, planar_stride;
 	int64_t stage_elems;
 	cudaStream_t s_copy, s_own, s_fir, s_trk;
 	cudaEvent_t ev_fir_done[2], ev_trk_done[2], ev_join;
@@ -201,6 +203,7 @@ extern "C" void gais_destroy(gais_ctx *ctx)
 	cudaFree(ctx->d_totals);
 	cudaFree(ctx->d_stage[0]);
 	cudaFree(ctx->d_stage[1]);
+	cudaFree(ctx->d_planar);
 	if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
 	if (ctx->s_own) cudaStreamDestroy(ctx->s_own);
 	if (ctx->s_fir) cudaStreamDestroy(ctx->s_fir);
@@ -385,14 +388,43 @@ static int enqueue_post(gais_ctx *ctx, cudaStream_t st)
 	return 0;
 }
 
+/* interleaved batches of at least 32 channels are copied into planar rows per tile (deinterleave_kernel: one more pass over
+ * the tile in HBM, 4 B per sample, against the 64 dependent FP32 operations per sample of the exact FIR kernel on strided loads);
+ * the reference's own stereo shape (2 channels) stays on the generic kernels */
+static bool relay_planar(const gais_ctx *ctx, const SampleView &view)
+{
+	return ctx->cfg.layout == GAIS_LAYOUT_INTERLEAVED && view.ch_stride == 1 && ctx->n_ch >= 32 && ctx->cfg.fir_mode == GAIS_FIR_GUARD;
+}
+
+static int ensure_planar(gais_ctx *ctx, int64_t tile_frames)
+{
+	const int64_t stride = (tile_frames + 7) / 8 * 8, need = stride * ctx->n_ch;
+	if (need <= ctx->planar_elems) {
+		return 0;
+	}
+	CK(cudaDeviceSynchronize());
+	cudaFree(ctx->d_planar);
+	ctx->d_planar = NULL;
+	ctx->planar_elems = 0;
+	cudaError_t e = cudaMalloc(&ctx->d_planar, (size_t) need * 2);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		return fail(e == cudaErrorMemoryAllocation ? GAIS_ENOMEM : GAIS_ECUDA, "planar copy of an interleaved tile (%lld samples x %d channels): %s",
+			    (long long) stride, ctx->n_ch, cudaGetErrorString(e));
+	}
+	ctx->planar_elems = need;
+	ctx->planar_stride = stride;
+	return 0;
+}
+
 /* which part of a tile the fused kernel takes: channels [0, ch) x samples [0, frames) (0, 0: none) */
 struct FusedPart { int ch; int64_t frames; };
 
 static FusedPart fused_part(const gais_ctx *ctx, const SampleView &view, int64_t n_frames)
 {
 	FusedPart p = { 0, 0 };
-	const bool aligned = ctx->cfg.layout == GAIS_LAYOUT_PLANAR && view.t_stride == 1 && (view.ch_stride % 8) == 0 &&
-			     ((uintptr_t) view.base % 16) == 0;
+	/* planar rows, or an interleaved batch that enqueue_tile() will re-lay as planar rows first */
+	const bool aligned = (view.t_stride == 1 && (view.ch_stride % 8) == 0 && ((uintptr_t) view.base % 16) == 0) || relay_planar(ctx, view);
 	/* small batches stay on the two kernels: below two channel sets per SM the chain is paced by one tracker warp walking
 	 * its block alone either way, and the stand-alone tracker (79 registers, no ring hand-over) walks it faster
 	 * (1024 channels x 480000: 10.4 vs 13.0 ms, profiles/r2_fused_experiments.txt) */
@@ -449,6 +481,18 @@ static int enqueue_tile(gais_ctx *ctx, SampleView view, int64_t n_frames, int ti
 	 * forth with events. */
 	const bool overlap = st != st_trk;
 	const bool keep = (ctx->cfg.flags & GAIS_KEEP_SIGNS) != 0;
+	int layout = ctx->cfg.layout;
+	if (relay_planar(ctx, view) && ctx->d_planar && n_frames <= ctx->planar_stride) {
+		dim3 grid((unsigned) ((ctx->n_ch + 31) / 32), (unsigned) ((n_frames + 63) / 64));
+		/* (every reader of the previous tile's planar copy -- FIR, history, peak -- is ahead of this launch on the same stream;
+		 * the tracking stage reads sign words only) */
+		deinterleave_kernel<<<grid, 256, 0, st>>>(view.base, view.t_stride, ctx->n_ch, n_frames, ctx->d_planar, ctx->planar_stride);
+		ctx->launches++;
+		view.base = ctx->d_planar;
+		view.ch_stride = ctx->planar_stride;
+		view.t_stride = 1;
+		layout = GAIS_LAYOUT_PLANAR;
+	}
 	const FusedPart fp = overlap ? FusedPart{ 0, 0 } : fused_part(ctx, view, n_frames);
 	uint32_t *signs;
 	if (keep)
@@ -484,7 +528,7 @@ static int enqueue_tile(gais_ctx *ctx, SampleView view, int64_t n_frames, int ti
 			ctx->launches++;
 		}
 	} else {
-		nl = fir_launch(ctx->cfg.fir_mode, ctx->cfg.layout, view, ctx->d_state, ctx->hist_sel, ctx->n_ch, n_frames, signs, st, &hist_saved);
+		nl = fir_launch(ctx->cfg.fir_mode, layout, view, ctx->d_state, ctx->hist_sel, ctx->n_ch, n_frames, signs, st, &hist_saved);
 		if (nl < 0)
 			return fail(GAIS_ECUDA, "FIR launch failed: %s", cudaGetErrorString(cudaGetLastError()));
 		ctx->launches += nl;
@@ -582,9 +626,12 @@ extern "C" int gais_run_device(gais_ctx *ctx, const int16_t *d_samples, int64_t 
 	int64_t tile = ctx->tile_frames;
 	const bool keep = (ctx->cfg.flags & GAIS_KEEP_SIGNS) != 0;
 	const FusedPart fp0 = fused_part(ctx, v0, n_frames < tile ? n_frames : tile);
-	const bool fused_all = fp0.ch == ctx->n_ch && !keep;
+	const bool relay = relay_planar(ctx, v0);
+	const bool fused_all = fp0.ch == ctx->n_ch && !keep && !relay;
 	if (fused_all)
 		tile = X_MAX_FRAMES;
+	if (relay && (rc = ensure_planar(ctx, n_frames < tile ? n_frames : tile)) != 0)
+		return rc;
 	int n_tiles = (int) ((n_frames + tile - 1) / tile);
 	if ((rc = ensure_tile_events(ctx, n_tiles)) != 0)
 		return rc;
@@ -669,6 +716,8 @@ extern "C" int gais_run_host(gais_ctx *ctx, const int16_t *h_samples, int64_t n_
 		int64_t words = tile_sign_words(ctx, fused_part(ctx, sv, nf0), nf0);
 		const int64_t wl = tile_sign_words(ctx, fused_part(ctx, sv, nfl), nfl);
 		if ((rc = ensure_signs(ctx, wl > words ? wl : words)) != 0)
+			return rc;
+		if (relay_planar(ctx, sv) && (rc = ensure_planar(ctx, nf0)) != 0)
 			return rc;
 	}
 	CK(cudaEventRecord(ctx->ev[EV_START], st));

@@ -116,6 +116,34 @@ __global__ void save_hist_kernel(SampleView in, ChanState *st, int hist_sel, int
 		st[c].hist[hist_sel ^ 1][i] = v[i];
 }
 
+/* Frame-interleaved samples [time][t_stride] (the reference's own buffer shape, src/receiver.c:102: channel c of frame n at
+ * buf[n * num_ch + c]) -> planar rows [channel][out_stride], so that batches of interleaved channels take the same fast kernels
+ * as planar input.  One block moves a 32-channel x 64-sample tile through shared memory (both sides in 64- / 128-byte runs). */
+__global__ void __launch_bounds__(256)
+deinterleave_kernel(const int16_t *__restrict__ in, int64_t t_stride, int n_channels, int64_t n_frames, int16_t *__restrict__ out,
+		    int64_t out_stride)
+{
+	__shared__ int16_t tile[64][33];
+	const int c0 = blockIdx.x * 32;
+	const int64_t n0 = (int64_t) blockIdx.y * 64;
+	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+	for (int i = ty; i < 64; i += 8) {
+		const int64_t n = n0 + i;
+		tile[i][tx] = (n < n_frames && c0 + tx < n_channels) ? in[n * t_stride + c0 + tx] : (int16_t) 0;
+	}
+	__syncthreads();
+	for (int i = ty; i < 32; i += 8) {
+		const int c = c0 + i;
+		if (c >= n_channels)
+			continue;
+		int16_t *row = out + (int64_t) c * out_stride + n0;
+		if (n0 + tx < n_frames)
+			row[tx] = tile[tx][i];
+		if (n0 + 32 + tx < n_frames)
+			row[32 + tx] = tile[32 + tx][i];
+	}
+}
+
 /* The level filter_run_buf() returns (src/filter.c:112-119): the maximum of the samples of the call, starting from
  * 0 -- i.e. positive samples only, SURVEY.md H6 -- which receiver_run() turns into the "Level on ch" log line
  * (src/receiver.c:137-147).  Optional (GAIS_KEEP_PEAK): one warp per channel, max-combined over the tiles of a run. */

@@ -130,3 +130,23 @@ def test_default_chain_choice():
                 r.run(d)
             assert rx.timing()["launches"] == (rf if fused else r2).timing()["launches"]
             assert rf.timing()["launches"] < r2.timing()["launches"]
+
+
+@pytest.mark.parametrize("chain", ["fused", "two_kernel"])
+def test_interleaved_batches_take_the_fast_kernels(chain):
+    """the reference's own buffer shape (frame-interleaved, src/receiver.c:102) with many channels: 70 channels x 33000
+    samples, device and host buffers, several tiles; the tile is re-laid as planar rows on the device and goes through the
+    same kernels as planar input -- everything equal to the oracle, and no slower path's launch count (the exact FIR
+    kernel would add launches per tile for every channel)"""
+    torch = torch_dev()
+    n_ch, n = 70, 33000
+    planar = synth_host(SynthParams(seed=88, sigma=300.0, rho=0.7), n_ch, n)
+    inter = np.ascontiguousarray(planar.T)                      # [n, n_ch]
+    want = oracle_all(planar)
+    for host in (False, True):
+        with BatchReceiver(n_ch, n, layout="interleaved", keep_bits=True, keep_signs=True, chain=chain, tile_frames=8192) as rx:
+            rx.run(inter if host else torch.from_numpy(inter).cuda())
+            res = dict(msgs=[rx.messages()], nmea_recs=[rx.nmea_records()], counters=rx.counters(), state=rx.state(),
+                       bits=rx.bits(), signs=rx.signs(n))
+        for c, w in enumerate(want):
+            check_channel(res, c, w)

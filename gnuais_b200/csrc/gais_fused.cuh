@@ -7,29 +7,35 @@
  * Why one kernel.  As two kernels (gais_fir_tc.cuh, gais_track.cuh) the FIR is bound by a chain of short
  * waits (mbarrier round trips, tcgen05.ld, TMA latency; issue slots 60 % used) and the tracker by the serial
  * per-channel dependency chains of 3.5 warps per scheduler (56 % used); each leaves about half of the issue
- * slots idle, and they cannot share an SM (4 FIR CTAs take all 512 TMEM columns and 61 K registers), so a step
+ * slots idle, and they cannot share an SM (4 FIR CTAs take all 512 TMEM columns and 59 K registers), so a step
  * costs the SUM of the two (profiles/r2_ncu_two_kernels.txt).  Here both halves are warps of the same CTA:
- * one CTA per SM owns up to 15 channel sets (32 channels each = one tracker warp each) for the whole run, and
+ * one CTA per SM owns up to X_SETS channel sets (32 channels each = one tracker warp each) for the whole run, and
  * the FIR half works through its 2 x sets channel groups round robin, one 256-sample stage at a time, so every
  * tracker warp gets a new block of 8 sign words each round.
  *
- * Warps of a CTA (4 + 4 X_EPI + 16):
- *   0, 1, 3 flip: bit 7 of every sample of a landed stage, in place (see gais_fir_tc.cuh), every third item each;
- *           on a group's first stage they also drop the carried history into the zero-filled block
- *   12      resolver: once per round, settles the outputs the integer contraction left open (tiers 2/3 of
+ * Warps of a CTA (28 by default: 72 registers per thread):
+ *   0       MMA issue: the whole warp walks the loop, one elected lane issues the six tcgen05.mma of every item
+ *           (4 accumulator slots of 128 TMEM columns, so the tensor core never waits for an epilogue); on a group's
+ *           first stage the warp first drops the carried history into the block TMA zero-filled
+ *   1       resolver: once per round, settles the outputs the integer contraction left open (tiers 2/3 of
  *           gais_fir.cuh from global memory, ~2.6e-4 of noisy audio) and clears their provisional 1 bits
- *   2       the three tcgen05.mma of every stage, by one elected lane (4 accumulator slots of 128 TMEM columns,
- *           so the tensor core never waits for an epilogue)
- *   4..11   epilogue: TMEM -> Q -> one sign word per thread (warp w: TMEM lane quadrant w % 4, the items of parity
- *           (w - 4) / 4) -> sign ring [set][slot][channel][word]
- *   13..27  trackers: one warp per channel set, one lane per channel: the loop of gais_track.cuh's
+ *   4..15   epilogue: TMEM -> Q -> one sign word per thread (warp w: TMEM lane quadrant w % 4, the items
+ *           k = (w - 4) / 4 mod X_EPI) -> sign ring [set][slot][channel][word]; its first lane also sends the TMA
+ *           request that refills the input slot whose MMAs it has just seen complete
+ *   2, 3, 16..27  trackers: one warp per channel set, one lane per channel: the loop of gais_track.cuh's
  *           track_kernel, reading its sign words from the ring
  *
+ * The samples go to the tensor core as they land: no thread touches them.  An int16 is 256 hi + lo with hi its SIGNED
+ * high byte and lo its UNSIGNED low byte, and one MMA has one A type, so every stage is multiplied twice -- as s8
+ * against taps that are zero at the low-byte positions, then as u8 against taps that are zero at the high-byte
+ * positions (see "no-flip operands" below).  The first version flipped bit 7 of every sample in place instead (both
+ * bytes signed, 3 MMAs: gais_fir_tc.cuh); its three flip warps cost 120 instructions per item and a pipeline stage,
+ * and the kernel is bound by instruction issue, not by the tensor pipe (profiles/r2_fused_experiments.txt).
+ *
  * Flow control is all mbarriers (no CTA-wide barrier after the set-up):
- *   in_full (TMA landed) -> in_flip (flipped) -> [issuer; also waits tmem_empty of the slot and
- *   sign_empty of the set's ring slot] -> mma_done (tcgen05.commit) -> [epilogue; its first lane also sends the TMA
- *   request that refills the input slot the MMAs have just finished with] -> tmem_empty, sign_pre (8 warp arrivals
- *   per set and round) -> [resolver] -> sign_ready -> [tracker] -> sign_empty.
+ *   in_full (TMA landed) -> [issuer; also waits tmem_empty of the slot and sign_empty of the set's ring block]
+ *   -> mma_done (tcgen05.commit) -> [epilogue] -> tmem_empty, sign_pre (8 warp arrivals per set and round)
+ *   -> [resolver] -> sign_ready -> [tracker] -> sign_empty.
  */
 #ifndef GAIS_FUSED_CUH
 #define GAIS_FUSED_CUH
@@ -39,7 +45,6 @@
 
 namespace gais {
 
-constexpr int X_SETS = 15;                       /* channel sets (32 channels) per CTA at most */
 #ifndef X_NS
 #define X_NS 8                                  /* input ring: stages of 9216 B */
 #endif
@@ -49,13 +54,10 @@ constexpr int X_SIGN_ROW = 9;                    /* words per channel in a block
 constexpr int X_SIGN_BLOCK = 32 * X_SIGN_ROW * 4;
 constexpr int X_QCAP = 192;                      /* open outputs per round (expected ~2 per set) */
 #ifndef X_DIAG
-#define X_DIAG 0                                 /* diagnostics builds only (wrong results): 1 no flip work, 2 no epilogue arithmetic, 4 trackers only consume */
+#define X_DIAG 0                                 /* diagnostics builds only (wrong results): 2 no epilogue arithmetic, 4 trackers only consume */
 #endif
 #ifndef X_SLEEP_EPI
-#define X_SLEEP_EPI 100                          /* ns between polls of a waiting epilogue / flip / tracker / resolver warp (0: bare try_wait loop) */
-#endif
-#ifndef X_SLEEP_FLIP
-#define X_SLEEP_FLIP 100
+#define X_SLEEP_EPI 100                          /* ns between polls of a waiting epilogue / tracker / resolver warp (0: bare try_wait loop) */
 #endif
 #ifndef X_SLEEP_TRK
 #define X_SLEEP_TRK 400
@@ -63,12 +65,20 @@ constexpr int X_QCAP = 192;                      /* open outputs per round (expe
 #ifndef X_EPI
 #define X_EPI 3                                  /* epilogue warps per TMEM lane quadrant: warp t takes the items k = t (mod X_EPI) */
 #endif
-constexpr int X_WARPS = 4 + 4 * X_EPI + 16, X_THREADS = X_WARPS * 32;
-constexpr int X_W_RES = 4 + 4 * X_EPI;           /* resolver warp; the trackers follow */
+#ifndef X_NWARPS
+#define X_NWARPS 28                              /* 28 warps leave 72 registers per thread, 32 leave 64 */
+#endif
+constexpr int X_WARPS = X_NWARPS, X_THREADS = X_WARPS * 32;
+constexpr int X_W_ISSUE = 0, X_W_RES = 1;        /* warps 2, 3 and 4 + 4 X_EPI .. are trackers; 4 .. 3 + 4 X_EPI the epilogue (TMEM quadrant = warp % 4) */
+constexpr int X_SETS = (X_WARPS - 4 * X_EPI - 2) < 16 ? (X_WARPS - 4 * X_EPI - 2) : 16;   /* channel sets (32 channels) per CTA at most */
+static_assert(X_SETS >= 1, "no tracker warps left");
 constexpr int X_MAX_FRAMES = 1 << 22;            /* per launch: sample indices travel in 23 bits */
 
 constexpr int XO_BMAT = 0;
-constexpr int XO_RING = XO_BMAT + U_BMAT_BYTES;
+constexpr int X_BL_K_BYTES = 64 * 32;                 /* one k-step of the low-byte pass's B: 64 rows x 32 bytes */
+constexpr int X_BL_BYTES = 3 * X_BL_K_BYTES;         /* 6144 */
+constexpr int X_BMAT_BYTES = U_BMAT_BYTES + X_BL_BYTES;
+constexpr int XO_RING = XO_BMAT + X_BMAT_BYTES;
 constexpr int XO_SIGN = XO_RING + X_NS * P_STAGE_BYTES;
 constexpr int XO_NTAB = XO_SIGN + X_SETS * X_D * X_SIGN_BLOCK;
 constexpr int XO_TAB = XO_NTAB + H_NSTATES * 16 * 4;
@@ -76,13 +86,55 @@ constexpr int XO_Q = XO_TAB + H_NSTATES * 2 * 2;
 constexpr int XO_QN = XO_Q + X_D * X_QCAP * 4;
 constexpr int XO_BAR = (XO_QN + X_D * 4 + 7) / 8 * 8;
 /* barrier indices */
-constexpr int XB_IN_FULL = 0, XB_IN_FLIP = XB_IN_FULL + X_NS, XB_MMA = XB_IN_FLIP + X_NS,
+constexpr int XB_IN_FULL = 0, XB_MMA = XB_IN_FULL + X_NS,
 	      XB_TMEM_EMPTY = XB_MMA + X_TS, XB_SIGN_PRE = XB_TMEM_EMPTY + X_TS, XB_SIGN_READY = XB_SIGN_PRE + X_SETS * X_D,
 	      XB_SIGN_EMPTY = XB_SIGN_READY + X_SETS * X_D, XB_COUNT = XB_SIGN_EMPTY + X_SETS * X_D;
 constexpr int X_SMEM_BYTES = XO_BAR + XB_COUNT * 8 + 1024;      /* + alignment slack */
 static_assert(XO_RING % 512 == 0 && P_STAGE_BYTES % 512 == 0, "ring slots must keep the swizzle phase");
 static_assert(X_SMEM_BYTES <= 227 * 1024, "shared memory");
 static_assert(X_NS % 2 == 0, "ring slots: an even number (refills keep their item parity)");
+
+/* ---- no-flip operands.  An int16 sample is 256 hi + lo with hi its SIGNED high byte and lo its UNSIGNED low byte, exactly; one
+ * MMA has one A type, so the stage is multiplied twice: as s8 with a tap matrix that is zero at the low-byte positions
+ * (D24 = sum T1 hi, D16 = sum T2 hi, D8 = sum T3 hi), then as u8 with one that is zero at the high-byte positions, accumulating
+ * into the last two slices (D16 += sum T1 lo, D8 += sum T2 lo).  sum T x = 2^24 D24 + 2^16 D16 + 2^8 D8 + D0 with
+ * 0 <= D0 = sum T3 lo <= 780300: dropped, its midpoint goes into the rounding constant (error +-0.0233 instead of the 0.0112 of
+ * the flipped form: |V / 65536 - R| < 0.0855 + 0.0018 + 0.0045 + 0.0233 = 0.1151 < U_VGUARD / 65536 = 0.125). ---- */
+__device__ uint8_t g_x_bmat_h[U_BMAT_BYTES];
+__device__ uint8_t g_x_bmat_l[X_BL_BYTES];
+constexpr int X_KC_NOFLIP = 32768 + 780300 / 512;     /* rounding + the midpoint of D0 / 256 */
+constexpr uint32_t X_IDESC_L = (2u << 4) | (0u << 7) | (0u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);   /* D s32, A u8, B u8, N 64, M 128 */
+
+static inline void x_build_taps_noflip(uint8_t *bh /* U_BMAT_BYTES */, uint8_t *bl /* X_BL_BYTES */)
+{
+	static const uint32_t half[18] = GAIS_TAP_BITS_HALF;
+	int64_t T[GAIS_NTAPS];
+	for (int i = 0; i < GAIS_NTAPS; i++) {
+		const uint32_t b = half[i < 18 ? i : 35 - i];
+		float t;
+		memcpy(&t, &b, 4);
+		T[i] = (i >= U_TAP_LO && i <= U_TAP_HI) ? (int64_t) ((double) t * 16777216.0 + 0.5) : 0;
+	}
+	memset(bh, 0, U_BMAT_BYTES);
+	memset(bl, 0, X_BL_BYTES);
+	for (int j = 0; j < 32; j++)
+		for (int sidx = 0; sidx < 48; sidx++) {
+			const int i = sidx - j + 12;
+			if (i < U_TAP_LO || i > U_TAP_HI)
+				continue;
+			const int Tb[3] = { (int) ((T[i] >> 16) & 255), (int) ((T[i] >> 8) & 255), (int) (T[i] & 255) };
+			/* high byte of sample sidx = byte 2 sidx + 1 of the window; low byte = byte 2 sidx (same canonical K-major layout as
+			 * umma_build_taps: 8-row groups 256 B apart, the two 16-byte K chunks of a group 128 B apart) */
+			for (int a = 0; a < 3; a++) {            /* s8 pass: rows 32 a + j, coefficient T(a+1) on the high byte */
+				const int n = 32 * a + j, k = 2 * sidx + 1, ks = k / 32, kk = k % 32;
+				bh[ks * U_BK_BYTES + (n / 8) * 256 + (kk / 16) * 128 + (n % 8) * 16 + kk % 16] = (uint8_t) Tb[a];
+			}
+			for (int a = 0; a < 2; a++) {            /* u8 pass: rows 32 a + j <-> slices D16, D8, coefficient T(a+1) on the low byte */
+				const int n = 32 * a + j, k = 2 * sidx, ks = k / 32, kk = k % 32;
+				bl[ks * X_BL_K_BYTES + (n / 8) * 256 + (kk / 16) * 128 + (n % 8) * 16 + kk % 16] = (uint8_t) Tb[a];
+			}
+		}
+}
 
 struct XArgs {
 	const int16_t *base;       /* sample (c, n) of the launch at base[c * ch_stride + n] */
@@ -317,7 +369,6 @@ ais_fused_kernel(const __grid_constant__ CUtensorMap tmap, const XArgs a)
 	if (tid == 0) {
 		for (int i = 0; i < X_NS; i++) {
 			mbar_init(bar_a + 8 * (XB_IN_FULL + i), 1);
-			mbar_init(bar_a + 8 * (XB_IN_FLIP + i), 1);
 		}
 		for (int i = 0; i < X_TS; i++) {
 			mbar_init(bar_a + 8 * (XB_MMA + i), 1);
@@ -332,8 +383,9 @@ ais_fused_kernel(const __grid_constant__ CUtensorMap tmap, const XArgs a)
 		for (int i = 0; i < X_D; i++)
 			reinterpret_cast<uint32_t *>(smem_g + XO_QN)[i] = 0;
 	}
-	for (int i = tid; i < U_BMAT_BYTES / 16; i += X_THREADS) {
-		const uint4 v = reinterpret_cast<const uint4 *>(g_umma_bmat)[i];
+	for (int i = tid; i < X_BMAT_BYTES / 16; i += X_THREADS) {
+		const uint4 v = i < U_BMAT_BYTES / 16 ? reinterpret_cast<const uint4 *>(g_x_bmat_h)[i]
+						      : reinterpret_cast<const uint4 *>(g_x_bmat_l)[i - U_BMAT_BYTES / 16];
 		asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(bmat_a + 16 * i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 	}
 	for (int i = tid; i < H_NSTATES * 16; i += X_THREADS)
@@ -350,7 +402,7 @@ ais_fused_kernel(const __grid_constant__ CUtensorMap tmap, const XArgs a)
 	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 	const uint32_t tmem = tmem_base_s;
 
-	if (warp == 2) {
+	if (warp == X_W_ISSUE) {
 		/* ===== MMA issue.  The whole warp walks the loop (uniform control flow: the waits and counters compile to a few
 		 * instructions; as one divergent lane the loop was 120 instructions of ELECT / R2UR / BRA.U.ANY per item and,
 		 * sharing its scheduler with six other warps, THE bottleneck of the first version at 1250 cycles per item,
@@ -369,7 +421,22 @@ ais_fused_kernel(const __grid_constant__ CUtensorMap tmap, const XArgs a)
 		int g = 0, s = 0;
 		uint32_t islot = 0, in_par = 0, tslot = 0, t_par = 1, sslot = 0, s_par = 1;     /* ring positions and the parities to wait for */
 		for (int k = 0; k < K; k++) {
-			mbar_wait(bar_a + 8 * (XB_IN_FLIP + islot), in_par);
+			mbar_wait(bar_a + 8 * (XB_IN_FULL + islot), in_par);
+			if (k < G) {
+				/* a group's first stage: TMA zero-filled the block before the launch's first sample; samples -32..-1 are
+				 * hist[4..35] (src/filter.c:129-134): 16 rows x 4 chunks of 16 B, written through the swizzle */
+				const int ch0 = (set0 + (k >> 1)) * 32 + (k & 1) * 16;
+#pragma unroll
+				for (int i = 0; i < 2; i++) {
+					const int idx = lane + 32 * i, row = idx >> 2, cc = idx & 3;
+					const uint32_t *h = reinterpret_cast<const uint32_t *>(a.st[ch0 + row].hist[a.hist_sel] + 4 + 8 * cc);
+					asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(swz64(ring_a + islot * P_STAGE_BYTES + row * P_ROW_BYTES + cc * 16)),
+						     "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3])
+						     : "memory");
+				}
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+				__syncwarp();
+			}
 			if (k >= X_TS)
 				mbar_wait(bar_a + 8 * (XB_TMEM_EMPTY + tslot), t_par);
 			if (s >= X_D && !(g & 1))        /* the tracker of this set has read the block that this stage's signs will overwrite */
@@ -386,6 +453,16 @@ ais_fused_kernel(const __grid_constant__ CUtensorMap tmap, const XArgs a)
 						"tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
 						::"r"(tmem + tslot * 128u), "l"(ad), "l"(bd), "r"(U_IDESC), "r"(kk ? 1u : 0u), "r"(0u) : "memory");
 				}
+				/* second pass: the same bytes as u8 against the low-byte taps, into the slices D16 and D8 (columns 32..95) */
+#pragma unroll
+				for (int kk = 0; kk < 3; kk++) {
+					const uint64_t ad = P_ADESC | (uint64_t) (((a0 + 32u * kk) & 0x3FFFFu) >> 4);
+					const uint64_t bd = U_BDESC | (uint64_t) (((bmat_a + (uint32_t) (U_BMAT_BYTES + kk * X_BL_K_BYTES)) & 0x3FFFFu) >> 4);
+					asm volatile(
+						"{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+						"tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+						::"r"(tmem + tslot * 128u + 32u), "l"(ad), "l"(bd), "r"(X_IDESC_L), "r"(1u), "r"(0u) : "memory");
+				}
 				asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_a + 8 * (XB_MMA + tslot)) : "memory");
 			}
 			__syncwarp();
@@ -396,54 +473,6 @@ ais_fused_kernel(const __grid_constant__ CUtensorMap tmap, const XArgs a)
 				s++;
 				if (++sslot == X_D) { sslot = 0; s_par ^= 1u; }
 			}
-		}
-	} else if (warp < 4) {
-		/* ===== flip: warps 0, 1, 3 take every third item each, a whole stage at a time (18 chunks of 16 B per lane).
-		 * Two warps sharing every item were the bottleneck of the bare pipeline: with the flip work compiled out it ran at
-		 * 406 instead of 707 cycles per item (profiles/r2_fused_experiments.txt) -- an item's flip is one long chain
-		 * (wait, LDS, XOR, STS, proxy fence, arrive), so what helps is more items in flight, not more lanes per item ===== */
-		const int fw = warp == 3 ? 2 : warp;
-		for (int k = fw; k < K; k += 3) {
-			const uint32_t slot = (uint32_t) k % X_NS, slot_a = ring_a + slot * P_STAGE_BYTES;
-			mbar_wait_sleep<X_SLEEP_FLIP>(bar_a + 8 * (XB_IN_FULL + slot), (uint32_t) (k / X_NS) & 1u);
-			if (X_DIAG & 1) {
-			} else if (k < G) {
-				/* a group's first stage: TMA zero-filled the block before the launch's first sample; samples -32..-1 are
-				 * hist[4..35] (src/filter.c:129-134).  swz64 is an involution on the slot offset: chunk p holds the
-				 * row bytes at offset swz64(16 p) */
-				const int ch0 = (set0 + (k >> 1)) * 32 + (k & 1) * 16;
-#pragma unroll 6
-				for (int i = 0; i < P_STAGE_CHUNKS / 32; i++) {
-					const uint32_t off = 16u * (32u * i + lane), lin = swz64(off);
-					const uint32_t row = lin / P_ROW_BYTES, col = lin % P_ROW_BYTES;
-					uint4 v;
-					if (col < 64u) {
-						const uint32_t *h = reinterpret_cast<const uint32_t *>(a.st[ch0 + row].hist[a.hist_sel] + 4 + (col >> 1));
-						v = make_uint4(h[0], h[1], h[2], h[3]);
-					} else
-						v = lds128(slot_a + off);
-					asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot_a + off), "r"(v.x ^ 0x00800080u),
-						     "r"(v.y ^ 0x00800080u), "r"(v.z ^ 0x00800080u), "r"(v.w ^ 0x00800080u)
-						     : "memory");
-				}
-			} else {
-#pragma unroll
-				for (int b = 0; b < 2; b++) {
-					uint4 v[9];
-#pragma unroll
-					for (int i = 0; i < 9; i++)
-						v[i] = lds128(slot_a + 16u * (32u * (9 * b + i) + lane));
-#pragma unroll
-					for (int i = 0; i < 9; i++)
-						asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot_a + 16u * (32u * (9 * b + i) + lane)),
-							     "r"(v[i].x ^ 0x00800080u), "r"(v[i].y ^ 0x00800080u), "r"(v[i].z ^ 0x00800080u), "r"(v[i].w ^ 0x00800080u)
-							     : "memory");
-				}
-			}
-			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-			__syncwarp();
-			if (lane == 0)
-				mbar_arrive(bar_a + 8 * (XB_IN_FLIP + slot));
 		}
 	} else if (warp == X_W_RES) {
 		/* ===== resolver ===== */
@@ -472,7 +501,7 @@ ais_fused_kernel(const __grid_constant__ CUtensorMap tmap, const XArgs a)
 			if (lane < n_sets)
 				mbar_arrive(bar_a + 8 * (XB_SIGN_READY + lane * X_D + slot));
 		}
-	} else if (warp >= 4 && warp < X_W_RES) {
+	} else if (warp >= 4 && warp < 4 + 4 * X_EPI) {
 		/* ===== epilogue: warp = (TMEM lane quadrant, item parity); both half words of every other item ===== */
 		const int qd = warp & 3, par = (warp - 4) >> 2;
 		const int m = 32 * qd + lane, c16 = m >> 3, r = m & 7;         /* MMA row: channel c16 of the group, word r of the stage */
@@ -529,9 +558,9 @@ ais_fused_kernel(const __grid_constant__ CUtensorMap tmap, const XArgs a)
 			g += X_EPI;
 			while (g >= G) { g -= G; s++; }
 		}
-	} else if (warp > X_W_RES) {
-		/* ===== trackers: warps 13..27 <-> sets 0..14 (14 sets per CTA at 65536 channels on 148 SMs: warp 27 idle) ===== */
-		const int set_l = warp - X_W_RES - 1;
+	} else {
+		/* ===== trackers: warps 2, 3 and the ones after the epilogue <-> sets 0, 1, 2 .. (14 sets per CTA at 65536 channels on 148 SMs) ===== */
+		const int set_l = warp < 4 ? warp - 2 : warp - 4 * X_EPI - 2;
 		if (set_l < n_sets)
 			x_track_role(a, (set0 + set_l) * 32 + lane, sign_a + set_l * X_D * X_SIGN_BLOCK, bar_a + 8 * (XB_SIGN_READY + set_l * X_D),
 				     bar_a + 8 * (XB_SIGN_EMPTY + set_l * X_D), ntab, tab);
@@ -545,6 +574,10 @@ ais_fused_kernel(const __grid_constant__ CUtensorMap tmap, const XArgs a)
 
 static inline int fused_setup(void)
 {
+	static uint8_t bh[U_BMAT_BYTES], bl[X_BL_BYTES];
+	x_build_taps_noflip(bh, bl);
+	if (cudaMemcpyToSymbol(g_x_bmat_h, bh, sizeof(bh)) != cudaSuccess || cudaMemcpyToSymbol(g_x_bmat_l, bl, sizeof(bl)) != cudaSuccess)
+		return -1;
 	return cudaFuncSetAttribute(ais_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, X_SMEM_BYTES) == cudaSuccess ? 0 : -1;
 }
 
@@ -570,7 +603,7 @@ static inline int fused_launch(SampleView view, ChanState *st, int hist_sel, int
 		spc = X_SETS;
 	a.sets_per_cta = spc;
 	a.save_hist = save_hist;
-	a.kc = g_umma_kc;
+	a.kc = X_KC_NOFLIP;
 	a.one = 1;
 	a.two16 = 65536;
 	a.out = out;

@@ -68,3 +68,37 @@ def test_integer_contraction_decides_like_the_reference():
     low = (p & 0xFFFF) - 32768
     frac_open = np.mean((q == 0) & (np.abs(low) < VGUARD))
     assert frac_open < 1e-3, frac_open
+
+
+def test_no_flip_contraction_decides_like_the_reference():
+    """the fused kernel's form (gais_fused.cuh, X_NOFLIP): the raw bytes multiplied twice -- high bytes as s8, low bytes as
+    u8 -- so x = 256 hi + lo exactly, no 128-offset; the dropped D0 = sum T3 lo is one-sided (0 .. 780300) and its midpoint
+    goes into the rounding constant"""
+    rng = np.random.default_rng(20261019)
+    win = windows(rng, 40000)
+    T = quantised_taps()
+    T1, T2, T3 = (T >> 16) & 255, (T >> 8) & 255, T & 255
+    xu = win.astype(np.uint16)
+    hi = (xu >> 8).astype(np.uint8).view(np.int8).astype(np.int64)
+    lo = (xu & 0xFF).astype(np.int64)
+    assert np.array_equal(256 * hi + lo, win.astype(np.int64))
+    d24 = (hi * T1).sum(axis=1)
+    d16 = (hi * T2).sum(axis=1) + (lo * T1).sum(axis=1)
+    d8 = (hi * T3).sum(axis=1) + (lo * T2).sum(axis=1)
+    d0 = (lo * T3).sum(axis=1)
+    for d in (d24, d16, d8):
+        assert np.abs(d).max() < 2 ** 31
+    assert d0.min() >= 0 and d0.max() <= 780300
+    r = reference_sum(win).astype(np.float64)
+    mid = 780300 // 512                                                       # X_KC_NOFLIP - 32768
+    v = 65536 * d24 + 256 * d16 + d8 + mid
+    err = np.abs(v / 65536.0 - r)
+    assert err.max() < 0.1151, err.max()
+    kc = 32768 + mid
+    p = 256 * d16 + d8 + kc
+    q = d24 + (p >> 16)
+    low = (p & 0xFFFF) - 32768
+    pos = (q >= 1) | ((q == 0) & (low >= VGUARD))
+    neg = (q <= -1) | ((q == 0) & (low <= -VGUARD))
+    assert pos.any() and neg.any() and (~(pos | neg)).any()
+    assert np.all(r[pos] > 0) and np.all(~(r[neg] > 0))

@@ -69,7 +69,10 @@ constexpr int X_QCAP = 192;                      /* open outputs per round (expe
 #define X_NWARPS 28                              /* 28 warps leave 72 registers per thread, 32 leave 64 */
 #endif
 constexpr int X_WARPS = X_NWARPS, X_THREADS = X_WARPS * 32;
-constexpr int X_W_ISSUE = 0, X_W_RES = 1;        /* warps 2, 3 and 4 + 4 X_EPI .. are trackers; 4 .. 3 + 4 X_EPI the epilogue (TMEM quadrant = warp % 4) */
+#ifndef X_RES_AT
+#define X_RES_AT (4 + 4 * X_EPI + 8)             /* the resolver's warp: same scheduler (warp % 4 == 0) as the issuer, which then shares it with two trackers only */
+#endif
+constexpr int X_W_ISSUE = 0, X_W_RES = X_RES_AT; /* 4 .. 3 + 4 X_EPI: epilogue (TMEM quadrant = warp % 4); every other warp is a tracker */
 constexpr int X_SETS = (X_WARPS - 4 * X_EPI - 2) < 16 ? (X_WARPS - 4 * X_EPI - 2) : 16;   /* channel sets (32 channels) per CTA at most */
 static_assert(X_SETS >= 1, "no tracker warps left");
 constexpr int X_MAX_FRAMES = 1 << 22;            /* per launch: sample indices travel in 23 bits */
@@ -560,7 +563,8 @@ ais_fused_kernel(const __grid_constant__ CUtensorMap tmap, const XArgs a)
 		}
 	} else {
 		/* ===== trackers: warps 2, 3 and the ones after the epilogue <-> sets 0, 1, 2 .. (14 sets per CTA at 65536 channels on 148 SMs) ===== */
-		const int set_l = warp < 4 ? warp - 2 : warp - 4 * X_EPI - 2;
+		const int set_l = warp < 4 ? warp - 1 - (X_W_RES < 4 && warp > X_W_RES ? 1 : 0)
+					   : warp - 4 * X_EPI - 4 + (X_W_RES < 4 ? 2 : 3) - (X_W_RES >= 4 && warp > X_W_RES ? 1 : 0);
 		if (set_l < n_sets)
 			x_track_role(a, (set0 + set_l) * 32 + lane, sign_a + set_l * X_D * X_SIGN_BLOCK, bar_a + 8 * (XB_SIGN_READY + set_l * X_D),
 				     bar_a + 8 * (XB_SIGN_EMPTY + set_l * X_D), ntab, tab);

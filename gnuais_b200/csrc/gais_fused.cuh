@@ -15,7 +15,7 @@
  *
  * Warps of a CTA (28 by default: 72 registers per thread):
  *   0       MMA issue: the whole warp walks the loop, one elected lane issues the six tcgen05.mma of every item
- *           (4 accumulator slots of 128 TMEM columns, so the tensor core never waits for an epilogue); on a group's
+ *           (5 accumulator slots of 96 TMEM columns, so the tensor core rarely waits for an epilogue); on a group's
  *           first stage the warp first drops the carried history into the block TMA zero-filled
  *   1       resolver: once per round, settles the outputs the integer contraction left open (tiers 2/3 of
  *           gais_fir.cuh from global memory, ~2.6e-4 of noisy audio) and clears their provisional 1 bits
@@ -48,7 +48,12 @@ namespace gais {
 #ifndef X_NS
 #define X_NS 8                                  /* input ring: stages of 9216 B */
 #endif
-constexpr int X_TS = 4;                          /* accumulator slots in TMEM (128 columns each) */
+#ifndef X_TSLOTS
+#define X_TSLOTS 5                               /* 5 x 96 columns: 2.98 ms on the quick workload, 4 x 128: 3.02, 3: 3.17 */
+#endif
+constexpr int X_TS = X_TSLOTS;                   /* accumulator slots in TMEM */
+constexpr uint32_t X_TCOLS = X_TSLOTS <= 4 ? 128u : 96u;   /* columns per slot (96 used) */
+static_assert(X_TSLOTS * (X_TSLOTS <= 4 ? 128 : 96) <= 512, "TMEM columns");
 constexpr int X_D = 4;                           /* sign ring: blocks of 8 words per channel set */
 constexpr int X_SIGN_ROW = 9;                    /* words per channel in a block: 8 + 1 (lanes 9 words apart: no bank conflicts) */
 constexpr int X_SIGN_BLOCK = 32 * X_SIGN_ROW * 4;
@@ -454,7 +459,7 @@ ais_fused_kernel(const __grid_constant__ CUtensorMap tmap, const XArgs a)
 					asm volatile(
 						"{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
 						"tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-						::"r"(tmem + tslot * 128u), "l"(ad), "l"(bd), "r"(U_IDESC), "r"(kk ? 1u : 0u), "r"(0u) : "memory");
+						::"r"(tmem + tslot * X_TCOLS), "l"(ad), "l"(bd), "r"(U_IDESC), "r"(kk ? 1u : 0u), "r"(0u) : "memory");
 				}
 				/* second pass: the same bytes as u8 against the low-byte taps, into the slices D16 and D8 (columns 32..95) */
 #pragma unroll
@@ -464,7 +469,7 @@ ais_fused_kernel(const __grid_constant__ CUtensorMap tmap, const XArgs a)
 					asm volatile(
 						"{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
 						"tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-						::"r"(tmem + tslot * 128u + 32u), "l"(ad), "l"(bd), "r"(X_IDESC_L), "r"(1u), "r"(0u) : "memory");
+						::"r"(tmem + tslot * X_TCOLS + 32u), "l"(ad), "l"(bd), "r"(X_IDESC_L), "r"(1u), "r"(0u) : "memory");
 				}
 				asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_a + 8 * (XB_MMA + tslot)) : "memory");
 			}
@@ -522,7 +527,7 @@ ais_fused_kernel(const __grid_constant__ CUtensorMap tmap, const XArgs a)
 				if (g2 >= G) { g2 -= G; s2++; }
 				x_load(tmap, bar_a, ring_a, set0, k + X_NS, g2, s2);
 			}
-			const uint32_t taddr = taddr0 + tslot * 128u;
+			const uint32_t taddr = taddr0 + tslot * X_TCOLS;
 			const int set_l = g >> 1, chl = (g & 1) * 16 + c16;
 			const uint32_t slot = (uint32_t) s % X_D;
 			uint32_t word = 0;

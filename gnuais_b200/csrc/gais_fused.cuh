@@ -54,7 +54,10 @@ namespace gais {
 constexpr int X_TS = X_TSLOTS;                   /* accumulator slots in TMEM */
 constexpr uint32_t X_TCOLS = X_TSLOTS <= 4 ? 128u : 96u;   /* columns per slot (96 used) */
 static_assert(X_TSLOTS * (X_TSLOTS <= 4 ? 128 : 96) <= 512, "TMEM columns");
-constexpr int X_D = 4;                           /* sign ring: blocks of 8 words per channel set */
+#ifndef X_DEPTH
+#define X_DEPTH 4
+#endif
+constexpr int X_D = X_DEPTH;                           /* sign ring: blocks of 8 words per channel set */
 constexpr int X_SIGN_ROW = 9;                    /* words per channel in a block: 8 + 1 (lanes 9 words apart: no bank conflicts) */
 constexpr int X_SIGN_BLOCK = 32 * X_SIGN_ROW * 4;
 constexpr int X_QCAP = 192;                      /* open outputs per round (expected ~2 per set) */

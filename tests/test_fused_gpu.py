@@ -93,7 +93,7 @@ def test_fused_chain_streams_and_host_buffers():
 
 
 def test_fused_chain_equals_two_kernel_chain_many_sets():
-    """71088 channels = 2221 sets + 16 leftover channels: more sets than one CTA per SM can own (15 x 148 = 2220), so the
+    """71088 channels = 2221 sets + 16 leftover channels: more sets than one CTA per SM can own (14 x 148 = 2072), so the
     grid does not fit one wave; records, counters and state equal the two-kernel chain's, a sample of channels equals
     the oracle"""
     torch = torch_dev()

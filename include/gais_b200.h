@@ -98,7 +98,8 @@ typedef struct gais_msg {
 	                         bit 4: type gate passed (1 <= type <= 24 -> NMEA is emitted) */
 	uint16_t nbits;       /* bufferpos - 22 of src/protodec.c:1096 (payload bits incl. a ragged tail) */
 	uint32_t channel;     /* channel index inside the batch (+ gais_config.reserved[3] when the batch is sharded) */
-	uint32_t end_bit;     /* index of the NRZI bit that closed the frame, counted per channel since create/reset */
+	uint32_t end_bit;     /* index of the NRZI bit that closed the frame, counted per channel since create/reset, modulo 2^32
+	                         (about 5.2 days of audio at 9600 bit/s: monotonic within a run, compare across runs with wrap-safe arithmetic) */
 } gais_msg;
 
 /* per-channel frame counters: receivedframes, lostframes (CRC), lostframes2 (size/stop bit) */
@@ -113,7 +114,7 @@ typedef struct gais_chan_state {
 	int32_t prev, lastbit;
 	int32_t fsm_state;   /* ST_SKURR=1 .. ST_STOPSIGN=5 (src/protodec.h:30-34) */
 	int32_t seqnr;
-	uint32_t n_bits;     /* NRZI bits produced since create/reset */
+	uint32_t n_bits;     /* NRZI bits produced since create/reset, modulo 2^32 */
 } gais_chan_state;
 
 /* fixed-stride NMEA text produced on the GPU: up to two "!AIVDM...\r\n" sentences per message */

@@ -150,3 +150,26 @@ def test_interleaved_batches_take_the_fast_kernels(chain):
                        bits=rx.bits(), signs=rx.signs(n))
         for c, w in enumerate(want):
             check_channel(res, c, w)
+
+
+def test_fused_chain_runs_longer_than_one_launch():
+    """a run of 2^22 + 5696 samples: the fused kernel takes at most 2^22 samples per launch (sample indices travel in 23 bits), so
+    the run is cut in two launches with history, DPLL phase and open frames carried across the cut; 35 channels (one whole set +
+    3 left over).  Equal to the two-kernel chain everywhere and to the oracle on a sample of channels."""
+    torch = torch_dev()
+    n_ch, n = 35, (1 << 22) + 5696
+    p = SynthParams(seed=512, sigma=300.0, rho=0.6)
+    d = torch.empty((n_ch, n), dtype=torch.int16, device="cuda")
+    synth_device(p, d, n_ch, n)
+    out = {}
+    for chain in ("fused", "two_kernel"):
+        with BatchReceiver(n_ch, n, chain=chain) as rx:
+            rx.run(d)
+            out[chain] = (rx.messages(), rx.counters(), rx.state(), rx.nmea_records())
+    a, b = out["fused"], out["two_kernel"]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert len(a[0]) > 10000
+    res = dict(msgs=[a[0]], nmea_recs=[a[3]], counters=a[1], state=a[2])
+    for c in (0, 31, 33):
+        w = O.port().run(d[c].cpu().numpy(), want_bits=False, want_signs=False)
+        check_channel(res, c, w, bits=False, signs=False)

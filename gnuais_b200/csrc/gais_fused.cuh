@@ -416,7 +416,7 @@ ais_fused_kernel(const __grid_constant__ CUtensorMap tmap, const XArgs a)
 		}
 		for (int i = 0; i < X_SETS * X_D; i++) {
 			mbar_init(bar_a + 8 * (XB_SIGN_PRE + i), X_ALL_ARRIVE ? 256 : 8);      /* 2 groups x 4 quadrant warps */
-			mbar_init(bar_a + 8 * (XB_SIGN_READY + i), 1);
+			mbar_init(bar_a + 8 * (XB_SIGN_READY + i), 32);
 			mbar_init(bar_a + 8 * (XB_SIGN_EMPTY + i), X_ALL_ARRIVE ? 32 : 1);
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -518,9 +518,10 @@ ais_fused_kernel(const __grid_constant__ CUtensorMap tmap, const XArgs a)
 		/* ===== resolver ===== */
 		for (int s = 0; s < a.n_stages; s++) {
 			const uint32_t slot = (uint32_t) s % X_D, par = ((uint32_t) s / X_D) & 1u;
-			if (lane < n_sets)
-				mbar_wait_sleep<X_SLEEP_TRK>(bar_a + 8 * (XB_SIGN_PRE + lane * X_D + slot), par);
-			__syncwarp();
+			/* every lane waits for every set's block itself: each lane then has its own acquire on the arrivals of the epilogue
+			 * threads whose queue entries and sign words it may touch (no reliance on ordering handed on through __syncwarp) */
+			for (int i = 0; i < n_sets; i++)
+				mbar_wait_sleep<X_SLEEP_TRK>(bar_a + 8 * (XB_SIGN_PRE + i * X_D + slot), par);
 			const uint32_t nq = min(lds32(qn_a + 4u * slot), (uint32_t) X_QCAP);
 			for (uint32_t e = lane; e < nq; e += 32u) {
 				const uint32_t item = lds32(q_a + 4u * (slot * X_QCAP + e));
@@ -537,9 +538,9 @@ ais_fused_kernel(const __grid_constant__ CUtensorMap tmap, const XArgs a)
 			__syncwarp();
 			if (lane == 0 && nq)
 				asm volatile("st.shared.u32 [%0], %1;" ::"r"(qn_a + 4u * slot), "r"(0u) : "memory");
-			__syncwarp();
-			if (lane < n_sets)
-				mbar_arrive(bar_a + 8 * (XB_SIGN_READY + lane * X_D + slot));
+			/* ... and every lane arrives on every set's barrier (count 32): its own release covers the bits it cleared */
+			for (int i = 0; i < n_sets; i++)
+				mbar_arrive(bar_a + 8 * (XB_SIGN_READY + i * X_D + slot));
 		}
 	} else if (warp >= X_EPI_BASE && warp < X_EPI_BASE + 4 * X_EPI) {
 		/* ===== epilogue: warp = (TMEM lane quadrant, item parity); both half words of every other item ===== */

@@ -87,7 +87,10 @@ constexpr int X_WARPS = X_NWARPS, X_THREADS = X_WARPS * 32;
 #ifndef X_LAYOUT
 #define X_LAYOUT 0
 #endif
-#if X_LAYOUT == 1
+#if X_LAYOUT == 3
+constexpr int X_EPI_BASE = 0;                               /* epilogue = warps 0 .. 11, every tracker above it */
+constexpr int X_W_ISSUE = 4 * X_EPI, X_W_RES = 4 * X_EPI + 4;   /* 12, 16: the same scheduler */
+#elif X_LAYOUT == 1
 constexpr int X_EPI_BASE = X_NWARPS - 4 - 4 * X_EPI;        /* 12: epilogue = warps 12 .. 23 */
 constexpr int X_W_ISSUE = X_NWARPS - 4, X_W_RES = X_NWARPS - 3;   /* 24, 25; 26 and 27 are trackers, like 0 .. 11 */
 #else

@@ -34,8 +34,9 @@
  *
  * Flow control is all mbarriers (no CTA-wide barrier after the set-up):
  *   in_full (TMA landed) -> [issuer; also waits tmem_empty of the slot and sign_empty of the set's ring block]
- *   -> mma_done (tcgen05.commit) -> [epilogue] -> tmem_empty, sign_pre (8 warp arrivals per set and round)
+ *   -> mma_done (tcgen05.commit) -> [epilogue] -> tmem_empty, sign_pre (the 8 epilogue warps of a set's block)
  *   -> [resolver] -> sign_ready -> [tracker] -> sign_empty.
+ * Every lane that reads what another warp wrote waits on the mbarrier itself, every lane that wrote arrives itself.
  */
 #ifndef GAIS_FUSED_CUH
 #define GAIS_FUSED_CUH

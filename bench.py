@@ -625,7 +625,7 @@ FUSED_MAX_FRAMES = 1 << 22       # gais_fused.cuh X_MAX_FRAMES: samples per laun
 
 def fused_path(n_ch: int, fir_mode: str) -> bool:
     """mirror of the library's choice (gais_api.cu fused_part): the one-kernel chain takes planar, aligned input whose
-    channel count is a multiple of 32 and gives every SM at least two 32-channel sets, in guard mode, unless GAIS_FUSED=0
+    channel count is a multiple of 32 and gives every SM at least five 32-channel sets, in guard mode, unless GAIS_FUSED=0
     or an older FIR is selected for an A/B run"""
     mode = os.environ.get("GAIS_FUSED", "1")
     n_sms = 148
@@ -634,7 +634,7 @@ def fused_path(n_ch: int, fir_mode: str) -> bool:
         n_sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
     except Exception:
         pass
-    return (fir_mode == "guard" and n_ch % 32 == 0 and (mode == "2" or (mode == "1" and n_ch // 32 >= 2 * n_sms))
+    return (fir_mode == "guard" and n_ch % 32 == 0 and (mode == "2" or (mode == "1" and n_ch // 32 >= 5 * n_sms))
             and os.environ.get("GAIS_FIR_IMPL", "") in ("", "tc"))
 
 

@@ -282,7 +282,7 @@ extern "C" int gais_create(const gais_config *cfg, gais_ctx **out)
 	{
 		int64_t run_frames = cfg->max_frames_per_run;
 		/* which chain: reserved[4] 1 = the two kernels, 2 = the fused kernel wherever the input allows it, 0 = GAIS_FUSED
-		 * (same values; default 1... "auto": fused when the batch gives every SM at least two channel sets) */
+		 * (same values; default 1... "auto": fused when the batch gives every SM at least five channel sets) */
 		ctx->fused = cfg->reserved[4] == 1 ? 0 : cfg->reserved[4] == 2 ? 2 : (int) env_i64("GAIS_FUSED", 1);
 		if (fir_impl() != 2)
 			ctx->fused = 0;
@@ -425,10 +425,11 @@ static FusedPart fused_part(const gais_ctx *ctx, const SampleView &view, int64_t
 	FusedPart p = { 0, 0 };
 	/* planar rows, or an interleaved batch that enqueue_tile() will re-lay as planar rows first */
 	const bool aligned = (view.t_stride == 1 && (view.ch_stride % 8) == 0 && ((uintptr_t) view.base % 16) == 0) || relay_planar(ctx, view);
-	/* small batches stay on the two kernels: below two channel sets per SM the chain is paced by one tracker warp walking
-	 * its block alone either way, and the stand-alone tracker (79 registers, no ring hand-over) walks it faster
-	 * (1024 channels x 480000: 10.4 vs 13.0 ms, profiles/r2_fused_experiments.txt) */
-	const bool want = ctx->fused == 2 || (ctx->fused == 1 && ctx->n_ch / 32 >= 2 * ctx->n_sms);
+	/* small batches stay on the two kernels: with few channel sets per SM the chain is paced by tracker warps walking their
+	 * blocks nearly alone either way, and the stand-alone tracker (79 registers, no ring hand-over) walks them faster
+	 * (1024 channels x 480000: 10.4 vs 13.0 ms; 16384 channels: 4.00 vs 4.13 ms per 131072 samples; 32768: 5.23 vs 4.65 --
+	 * the fused kernel wins from about 4.5 sets per SM on, profiles/r2_fused_experiments.txt) */
+	const bool want = ctx->fused == 2 || (ctx->fused == 1 && ctx->n_ch / 32 >= 5 * ctx->n_sms);
 	if (want && ctx->cfg.fir_mode == GAIS_FIR_GUARD && aligned && n_frames <= X_MAX_FRAMES) {
 		p.ch = ctx->n_ch / 32 * 32;
 		p.frames = n_frames / P_T * P_T;

@@ -85,7 +85,7 @@ typedef struct gais_config {
 	                                   GPUs: gais_msg.channel = reserved[3] + local index;
 	                               [4] kernel chain: 1 = FIR-sign kernel + tracking kernel, 2 = the fused kernel wherever the
 	                                   input allows it (planar, 16-byte aligned rows, GAIS_FIR_GUARD), 0 = the fused kernel
-	                                   for batches of at least two 32-channel sets per SM (or what GAIS_FUSED says);
+	                                   for batches of at least five 32-channel sets per SM (or what GAIS_FUSED says);
 	                               [5..7] must be 0 */
 } gais_config;
 

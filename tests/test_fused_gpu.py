@@ -122,7 +122,7 @@ def test_default_chain_choice():
     torch = torch_dev()
     n_sms = torch.cuda.get_device_properties(0).multi_processor_count
     n = 4096
-    for n_ch, fused in ((1024, False), (2 * 32 * n_sms, True)):
+    for n_ch, fused in ((1024, False), (5 * 32 * n_sms, True)):
         d = torch.empty((n_ch, n), dtype=torch.int16, device="cuda")
         synth_device(SynthParams(seed=1, sigma=300.0, rho=0.5), d, n_ch, n)
         with BatchReceiver(n_ch, n) as rx, BatchReceiver(n_ch, n, chain="fused") as rf, BatchReceiver(n_ch, n, chain="two_kernel") as r2:
